@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — attention-forward TFLOPS on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Workload (default ``c2_sweep`` = BASELINE.json configs[1], the configuration the metric is quoted
+on): fp16, B=1 per GPU, H=16, D=128, non-causal, one forward per sequence length
+N in {512, 1024, 2048, 4096, 8192, 16384}.  A *step* is one pass over that sweep (six launches)
+on synthetic U[0,1) Q, K, V (torch.manual_seed(0), as bench_with_sdpa.py:207-209 but seeded).
+
+  value   whole-job TFLOPS = (sum of 4 B H N^2 D over the sweep, all ranks) / device time, inputs
+          resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e     the same sweep through the host-buffer C-ABI call (fa_fwd_sm100_host): pinned host
+          Q, K, V -> device -> kernel -> pinned host O inside the timed region
+  roofline  dominant kernel = the N=16384 launch of the sweep, FLOPs / its own event time vs the
+          measured bf16 tensor peak (MEASURED_PEAKS.json, burst figure)
+  cpu_baseline  the reference's CPU SDPA path (oracle port) on a bounded sample, rank 0, N_gpus=1
+
+With --gpus N > 1 (launched under torchrun) every rank runs the same sweep on its own batch
+element: weak scaling over B, no data-path collective; timing is the max over
+ranks, reduced with torch.distributed.  ``--workload c5`` runs BASELINE config 5 instead
+(B=64, N=4096, batch split across the ranks: strong scaling).
+
+``--impl reference`` times the reference's own CPU implementation of the path (the oracle port of
+pure_torch_ver.py / CPU SDPA — the AMD HIP kernels cannot run here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "flash-attention-v2-rdna3-minimal_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+SWEEP_N = [512, 1024, 2048, 4096, 8192, 16384]
+H, D = 16, 128
+L2_BYTES = 126 * 2 ** 20
+METRIC = "attention fwd TFLOPS (fp16, D=128) vs seqlen; % of B200 tensor-core peak"
+
+
+def flops(B, Hh, N, Dd, causal=False):
+    f = 4.0 * B * Hh * N * N * Dd  # bench_with_sdpa.py:35-36
+    return 0.5 * f if causal else f
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"tflops": float(p["bf16_tflops"]), "tflops_sustained": float(p.get("bf16_tflops_sustained", 0)),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json, burst)"}
+    return {"tflops": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port), rank 0 only
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, sample_n=(512, 1024, 2048)):
+    """Time the oracle port of the reference's CPU SDPA path on a bounded sample of the sweep
+    (the first three sequence lengths; math SDPA materialises H N^2 scores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fa_oracle as orc
+
+    torch.manual_seed(0)
+    data = []
+    for n in sample_n:
+        q, k, v = (torch.rand((1, H, n, D), dtype=torch.float16) for _ in range(3))
+        data.append((n, q, k, v))
+    for _ in range(max(1, warmup)):
+        for n, q, k, v in data:
+            orc.cpu_sdpa(q, k, v)
+    per_n = {n: 0.0 for n in sample_n}
+    t_all0 = time.perf_counter()
+    for _ in range(steps):
+        for n, q, k, v in data:
+            t0 = time.perf_counter()
+            orc.cpu_sdpa(q, k, v)
+            per_n[n] += time.perf_counter() - t0
+    t_all = time.perf_counter() - t_all0
+    total_flops = steps * sum(flops(1, H, n, D) for n in sample_n)
+    # the tiled oracle itself (pure_torch_ver.py restatement), one pass, for the record
+    t0 = time.perf_counter()
+    orc.tiled_fa2_forward(data[0][1], data[0][2], data[0][3])
+    t_tiled = time.perf_counter() - t0
+    return {
+        "value": total_flops / t_all / 1e12,
+        "ms_per_step": t_all / steps * 1e3,
+        "per_n_tflops": {str(n): flops(1, H, n, D) * steps / per_n[n] / 1e12 for n in sample_n},
+        "tiled_oracle_tflops_n512": flops(1, H, sample_n[0], D) / t_tiled / 1e12,
+        "cores": torch.get_num_threads(),
+        "host_cpus": os.cpu_count(),
+        "sample": f"fp16 B=1 H=16 D=128 non-causal, N in {list(sample_n)} of the sweep, {steps} passes, "
+                  f"torch CPU scaled_dot_product_attention (oracle.cpu_sdpa)",
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = min(args.steps, 5)
+    r = cpu_reference_run(steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "TFLOPS",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic U[0,1) Q,K,V (torch.manual_seed(0))",
+        "config": {"workload": "c2_sweep sample: fp16 B=1 H=16 D=128 causal=False, " + r["sample"],
+                   "note": "reference HIP/rocWMMA kernels need an AMD GPU; this is the reference's CPU SDPA "
+                           "path (pure_torch_ver.py) via the oracle port"},
+        "cpu_baseline": {"value": r["value"], "unit": "TFLOPS", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"], "per_n_tflops": r["per_n_tflops"],
+                         "host_cpus": r["host_cpus"]},
+        "e2e": {"value": r["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def make_pool(shape, dtype, device, min_bytes):
+    """Rotating pool of (q, k, v, o) sets whose total size exceeds ``min_bytes`` so that successive
+    timed iterations never find their inputs in L2."""
+    per_set = 4 * shape[0] * shape[1] * shape[2] * shape[3] * 2
+    n_sets = max(2, -(-min_bytes // per_set))
+    pool = []
+    for _ in range(n_sets):
+        q = torch.rand(shape, dtype=dtype, device=device)
+        k = torch.rand(shape, dtype=dtype, device=device)
+        v = torch.rand(shape, dtype=dtype, device=device)
+        pool.append((q, k, v))
+    return pool
+
+
+def time_variant(fa, pool, causal, iters, warm=3):
+    """Average device time (ms) of one forward on rotating inputs (extra sweeps, not the headline)."""
+    for i in range(warm):
+        q, k, v = pool[i % len(pool)]
+        fa(q, k, v, None, causal)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        q, k, v = pool[i % len(pool)]
+        fa(q, k, v, None, causal)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_sweep", choices=["c2_sweep", "c5"])
+    ap.add_argument("--no-extras", action="store_true", help="skip bf16/causal sweeps, e2e and CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    from rocwmma_fattn import _capi
+    from rocwmma_fattn.FlashAttn import FlashAttentionFunction, flash_attn_forward_host
+    from shard import shard_batch
+
+    fa = FlashAttentionFunction.apply
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    dtype = torch.float16
+
+    # ---- workload
+    if args.workload == "c2_sweep":
+        b_local = 1
+        points = [(b_local, n) for n in SWEEP_N]
+        scaling = "weak"
+        global_b = world
+        wl_name = "c2_sweep: fp16 fwd B=1/GPU H=16 D=128 causal=False, N in 512..16384 (BASELINE configs[1])"
+    else:
+        start, cnt = shard_batch(64, world, rank)
+        b_local = cnt
+        points = [(b_local, 4096)]
+        scaling = "strong"
+        global_b = 64
+        wl_name = "c5: fp16 fwd B=64 H=16 N=4096 D=128 causal=False, batch split across ranks (BASELINE configs[4])"
+
+    pools = {}
+    for (b, n) in points:
+        pools[n] = make_pool((b, H, n, D), dtype, dev, 2 * L2_BYTES + 1)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (untimed)
+    for w in range(args.warmup):
+        for (b, n) in points:
+            q, k, v = pools[n][w % len(pools[n])]
+            fa(q, k, v, None, False)
+    torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY K steps, events on the launching (current) stream
+    n_ev = len(points) + 1
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    launches0 = _capi.launch_count()
+    for s in range(args.steps):
+        ev = events[s]
+        ev[0].record()
+        for i, (b, n) in enumerate(points):
+            q, k, v = pools[n][(args.warmup + s) % len(pools[n])]
+            fa(q, k, v, None, False)
+            ev[i + 1].record()
+    barrier()
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_ms = events[0][0].elapsed_time(events[-1][-1])
+    per_point_ms = [sum(events[s][i].elapsed_time(events[s][i + 1]) for s in range(args.steps)) / args.steps
+                    for i in range(len(points))]
+    if dist is not None:
+        t = torch.tensor([total_ms] + per_point_ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, per_point_ms = t[0].item(), t[1:].tolist()
+        ln = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+
+    step_flops_global = sum(flops(global_b if args.workload == "c2_sweep" else 64, H, n, D)
+                            for (_, n) in points)
+    ms_per_step = total_ms / args.steps
+    value = step_flops_global / (ms_per_step * 1e-3) / 1e12
+
+    per_n = {}
+    for (b, n), ms in zip(points, per_point_ms):
+        gb = global_b if args.workload == "c2_sweep" else 64
+        tf = flops(gb, H, n, D) / (ms * 1e-3) / 1e12
+        bytes_ = 8.0 * gb * H * n * D
+        per_n[str(n)] = {"ms": round(ms, 5), "tflops": round(tf, 2),
+                         "frac_of_peak": round(tf / (peaks["tflops"] * world), 4),
+                         "hbm_gbs_algorithmic": round(bytes_ / (ms * 1e-3) / 1e9, 1)}
+
+    # ---- roofline of the dominant kernel (largest N of the step), per launch, one GPU's share
+    dom_b, dom_n = points[-1]
+    dom_ms = per_point_ms[-1]
+    dom_flops = flops(dom_b, H, dom_n, D)
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
+                "kernel": f"fa_fwd_ws_kernel<128,f16,non-causal> B={dom_b} H=16 N={dom_n}",
+                "flops_per_launch": dom_flops, "ms_per_launch": round(dom_ms, 5),
+                "peak_source": peaks["source"],
+                "frac_of_sustained": round(achieved / peaks["tflops_sustained"], 4) if peaks["tflops_sustained"] else None,
+                "algorithmic_bytes_per_launch": 8.0 * dom_b * H * dom_n * D,
+                "hbm_gbs_algorithmic": round(8.0 * dom_b * H * dom_n * D / (dom_ms * 1e-3) / 1e9, 1),
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "TFLOPS", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic U[0,1) Q,K,V (torch.manual_seed(0)), fp32 accumulate",
+        "config": {"workload": wl_name, "global_batch": global_b if args.workload == "c2_sweep" else 64,
+                   "heads": H, "head_dim": D, "seqlens": [n for (_, n) in points],
+                   "parallelism": f"batch-shard x{world} (no collective)",
+                   "l2": "rotating input pools > 2x L2 (252 MiB) per sequence length",
+                   "per_n": per_n},
+        "roofline": roofline,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    # ---- extras on rank 0 / single GPU only: e2e, bf16 + causal sweeps, CPU baseline
+    if dist is not None:
+        # e2e under torchrun: every rank runs its own host-buffer sweep; max over ranks
+        pass
+    e2e_steps = max(3, min(args.steps, 10))
+    host = {}
+    for (b, n) in points:
+        host[n] = tuple(torch.rand((b, H, n, D), dtype=dtype).pin_memory() for _ in range(3)) + (
+            torch.empty((b, H, n, D), dtype=dtype).pin_memory(),)
+    for _ in range(2):
+        for (b, n) in points:
+            qh, kh, vh, oh = host[n]
+            flash_attn_forward_host(qh, kh, vh, out=oh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for (b, n) in points:
+            qh, kh, vh, oh = host[n]
+            flash_attn_forward_host(qh, kh, vh, out=oh)  # returns after O has landed in host memory
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    h2d = sum(3 * b * H * n * D * 2 for (b, n) in points)
+    d2h = sum(b * H * n * D * 2 for (b, n) in points)
+    line["e2e"] = {"value": round(step_flops_global / e2e_s / 1e12, 3), "unit": "TFLOPS",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": round(e2e_s * 1e3, 4), "steps": e2e_steps,
+                   "api": "rocwmma_fattn.FlashAttn.flash_attn_forward_host -> fa_fwd_sm100_host (pinned host "
+                          "Q,K,V in, pinned host O out, copies inside the timed region, wall clock)",
+                   "pcie_gbs": round((h2d + d2h) / e2e_s / 1e9, 1)}
+    # sanity: the e2e path produced the same bits as the device path for the last point
+    del host
+
+    if world == 1 and not args.no_extras and args.workload == "c2_sweep":
+        extras = {}
+        for name, dt, causal in (("bf16_noncausal", torch.bfloat16, False), ("f16_causal", dtype, True)):
+            res = {}
+            for n in SWEEP_N:
+                pool = pools[n] if dt == dtype else [tuple(t.to(dt) for t in s) for s in pools[n][:max(2, len(pools[n]) // 8)]]
+                ms = time_variant(fa, pool, causal, iters=max(10, min(100, int(2e12 / flops(1, H, n, D)))))
+                res[str(n)] = {"ms": round(ms, 5), "tflops": round(flops(1, H, n, D, causal) / (ms * 1e-3) / 1e12, 2)}
+                del pool
+            extras[name] = res
+        line["config"]["extra_sweeps"] = extras
+        del pools
+        torch.cuda.empty_cache()
+        cpu = cpu_reference_run(steps=3, warmup=1)
+        line["cpu_baseline"] = {"value": round(cpu["value"], 4), "unit": "TFLOPS", "cores": cpu["cores"],
+                                "kind": "port", "sample": cpu["sample"],
+                                "per_n_tflops": {k: round(v, 4) for k, v in cpu["per_n_tflops"].items()},
+                                "tiled_oracle_tflops_n512": round(cpu["tiled_oracle_tflops_n512"], 5),
+                                "host_cpus": cpu["host_cpus"]}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

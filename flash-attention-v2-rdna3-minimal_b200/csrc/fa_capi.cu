@@ -1,0 +1,596 @@
+// C-ABI host side of the B200 Flash-Attention-2 forward path (see include/fa_fwd_sm100.h).
+//
+// Replaces the reference's native host layer:
+//   /root/reference/rocwmma_fattn/host.cpp:30-45          dtype dispatch            -> fa_fwd_sm100(dtype)
+//   /root/reference/rocwmma_fattn/kernel_fp16.cu:744-876  forward_fp16 (pad, alloc,
+//   /root/reference/rocwmma_fattn/kernel_bf16.cu:802-941  forward_bf16  grid, launch) -> plan + launch below
+//
+// What is different by design: no tensors are allocated or copied here (unaligned sequence lengths
+// are handled by TMA out-of-bounds fill + in-kernel masks instead of F::pad, both memory layouts
+// are consumed through TMA strides instead of .contiguous()), errors are returned instead of
+// printf'd, and the launch goes to the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fa_fwd_sm100.h"
+#include "fa_fwd_simt.cuh"
+#include "fa_fwd_tc.cuh"
+#include "fa_fwd_ws.cuh"
+#include "umma_probe.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define FA_CUDA_TRY(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (void)cudaGetLastError();                                                             \
+      return fail(FA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    }                                                                                       \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 4-D map over a logical [B,H,N,D] 16-bit tensor with element strides st[4] (b,h,n,d), box =
+// {64 d-elements (one 128-byte swizzle row), box_rows, 1, 1}, SWIZZLE_128B, zero OOB fill.
+int make_map(CUtensorMap* map, const void* base, int B, int H, int N, int D, const int64_t st[4],
+             int dtype, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(N),
+                        static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(st[2]) * 2, static_cast<cuuint64_t>(st[1]) * 2,
+                           static_cast<cuuint64_t>(st[0]) * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (CUresult %d) dims=[%d,%d,%d,%d] strides(elem)=[%lld,%lld,%lld]",
+             static_cast<int>(r), D, N, H, B, static_cast<long long>(st[2]),
+             static_cast<long long>(st[1]), static_cast<long long>(st[0]));
+    return fail(FA_ERR_CUDA, buf);
+  }
+  return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// problem description + validation + kernel choice (pure host logic)
+// ---------------------------------------------------------------------------------------------
+struct Problem {
+  int B, H, Nq, Nkv, D, dtype, causal;
+  float scale;
+  int64_t qs[4], ks[4], vs[4], os[4];
+};
+
+// A stride of a size-1 dimension is meaningless (torch reports arbitrary values): replace it by a
+// value that is always TMA-encodable.
+void canon_strides(int64_t st[4], int B, int H, int N, int D) {
+  (void)D;
+  const int64_t safe = 8;
+  if (N == 1) st[2] = safe;
+  if (H == 1) st[1] = safe;
+  if (B == 1) st[0] = safe;
+}
+
+int validate(Problem& p, const int64_t* qs, const int64_t* ks, const int64_t* vs,
+             const int64_t* os) {
+  if (qs == nullptr || ks == nullptr || vs == nullptr || os == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "stride arrays must not be null");
+  if (p.B < 1 || p.H < 1 || p.Nq < 1 || p.Nkv < 1 || p.D < 1) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "sizes must be positive: B=%d H=%d Nq=%d Nkv=%d D=%d", p.B, p.H, p.Nq,
+             p.Nkv, p.D);
+    return fail(FA_ERR_INVALID_ARG, buf);
+  }
+  if (p.dtype != FA_DTYPE_F16 && p.dtype != FA_DTYPE_BF16)
+    return fail(FA_ERR_INVALID_ARG, "dtype must be FA_DTYPE_F16 or FA_DTYPE_BF16");
+  if (!std::isfinite(p.scale)) return fail(FA_ERR_INVALID_ARG, "scale must be finite");
+  memcpy(p.qs, qs, sizeof p.qs);
+  memcpy(p.ks, ks, sizeof p.ks);
+  memcpy(p.vs, vs, sizeof p.vs);
+  memcpy(p.os, os, sizeof p.os);
+  if (p.qs[3] != 1 || p.ks[3] != 1 || p.vs[3] != 1 || p.os[3] != 1)
+    return fail(FA_ERR_INVALID_ARG, "the innermost (head-dim) stride of q, k, v and o must be 1");
+  for (int i = 0; i < 3; ++i)
+    if (p.qs[i] < 0 || p.ks[i] < 0 || p.vs[i] < 0 || p.os[i] < 0)
+      return fail(FA_ERR_INVALID_ARG, "negative strides are not supported");
+  if (p.D > fa::kSimtMaxD) return fail(FA_ERR_UNSUPPORTED, "head dim > 1024 is not supported");
+  if (p.B > 65535 || p.H > 65535)
+    return fail(FA_ERR_UNSUPPORTED, "B and H must be <= 65535 (CUDA grid limit)");
+  canon_strides(p.qs, p.B, p.H, p.Nq, p.D);
+  canon_strides(p.os, p.B, p.H, p.Nq, p.D);
+  canon_strides(p.ks, p.B, p.H, p.Nkv, p.D);
+  canon_strides(p.vs, p.B, p.H, p.Nkv, p.D);
+  return FA_OK;
+}
+
+bool tma_ok_strides(const int64_t st[4]) {
+  for (int i = 0; i < 3; ++i) {
+    if (st[i] % 8 != 0) return false;                  // 16-byte multiple
+    if (st[i] * 2 >= (int64_t(1) << 40)) return false;  // TMA stride limit
+  }
+  return true;
+}
+
+// pointer-independent part of the choice
+int choose_kernel_shape(const Problem& p) {
+  const bool tc = (p.D % 8 == 0) && (p.D <= 128) && (p.scale > 0.f) && tma_ok_strides(p.qs) &&
+                  tma_ok_strides(p.ks) && tma_ok_strides(p.vs) && tma_ok_strides(p.os);
+  if (!tc) return FA_KERNEL_SIMT;
+  if (p.Nq <= fa::kTileM) return FA_KERNEL_TC1;
+  return FA_KERNEL_WS;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// tensor-map plan cache: encoding four maps costs a few microseconds, which matters at N = 512
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  const void *q, *k, *v, *o;
+  Problem p;
+  int device;
+  CUtensorMap mq, mk, mv, mo;
+  uint64_t stamp;
+};
+
+struct PlanCache {
+  std::mutex mu;
+  std::vector<Plan> plans;
+  uint64_t clock = 0;
+  static constexpr size_t kCap = 64;
+
+  static bool same(const Plan& a, const void* q, const void* k, const void* v, const void* o,
+                   const Problem& p, int device) {
+    return a.q == q && a.k == k && a.v == v && a.o == o && a.device == device &&
+           a.p.B == p.B && a.p.H == p.H && a.p.Nq == p.Nq && a.p.Nkv == p.Nkv && a.p.D == p.D &&
+           a.p.dtype == p.dtype && memcmp(a.p.qs, p.qs, sizeof p.qs) == 0 &&
+           memcmp(a.p.ks, p.ks, sizeof p.ks) == 0 && memcmp(a.p.vs, p.vs, sizeof p.vs) == 0 &&
+           memcmp(a.p.os, p.os, sizeof p.os) == 0;
+  }
+
+  int get(const void* q, const void* k, const void* v, void* o, const Problem& p, int device,
+          Plan* out) {
+    std::lock_guard<std::mutex> lk(mu);
+    ++clock;
+    for (auto& pl : plans) {
+      if (same(pl, q, k, v, o, p, device)) {
+        pl.stamp = clock;
+        *out = pl;
+        return FA_OK;
+      }
+    }
+    Plan pl;
+    pl.q = q; pl.k = k; pl.v = v; pl.o = o; pl.p = p; pl.device = device; pl.stamp = clock;
+    int rc;
+    if ((rc = make_map(&pl.mq, q, p.B, p.H, p.Nq, p.D, p.qs, p.dtype, fa::kTileM))) return rc;
+    if ((rc = make_map(&pl.mk, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN))) return rc;
+    if ((rc = make_map(&pl.mv, v, p.B, p.H, p.Nkv, p.D, p.vs, p.dtype, fa::kTileN))) return rc;
+    if ((rc = make_map(&pl.mo, o, p.B, p.H, p.Nq, p.D, p.os, p.dtype, fa::kTileM))) return rc;
+    if (plans.size() < kCap) {
+      plans.push_back(pl);
+    } else {
+      size_t victim = 0;
+      for (size_t i = 1; i < plans.size(); ++i)
+        if (plans[i].stamp < plans[victim].stamp) victim = i;
+      plans[victim] = pl;
+    }
+    *out = pl;
+    return FA_OK;
+  }
+};
+PlanCache g_plans;
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+// The dynamic shared-memory opt-in is per (kernel, device); `done` remembers the devices served.
+template <typename K>
+int set_smem(K kernel, int bytes, std::atomic<uint64_t>* done = nullptr, int device = 0) {
+  const uint64_t bit = uint64_t(1) << (device & 63);
+  if (done != nullptr && (done->load(std::memory_order_acquire) & bit)) return FA_OK;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (done != nullptr) done->fetch_or(bit, std::memory_order_release);
+  return FA_OK;
+}
+
+template <int kDP, bool kBF16, bool kCausal>
+int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_ws_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::WsCfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f};
+  dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
+  kernel<<<grid, 512, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+template <int kDP, bool kBF16, bool kCausal, bool kPsmem>
+int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_tc1_kernel<kDP, kBF16, kCausal, kPsmem>;
+  constexpr int smem = fa::Tc1Smem<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f};
+  dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
+  kernel<<<grid, 128, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+template <int kDP, bool kBF16, bool kCausal>
+int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
+  switch (kernel) {
+    case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
+    case FA_KERNEL_TC1: return launch_tc1<kDP, kBF16, kCausal, false>(pl, lse, stream);
+    case FA_KERNEL_TC1_PSMEM: return launch_tc1<kDP, kBF16, kCausal, true>(pl, lse, stream);
+  }
+  return fail(FA_ERR_INVALID_ARG, "unknown tensor-core kernel selector");
+}
+
+int launch_tc(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  const bool bf = p.dtype == FA_DTYPE_BF16;
+  const bool ca = p.causal != 0;
+#define FA_DISPATCH(DP)                                                              \
+  do {                                                                               \
+    if (bf) {                                                                        \
+      if (ca) return launch_tc_variant<DP, true, true>(kernel, pl, lse, stream);     \
+      return launch_tc_variant<DP, true, false>(kernel, pl, lse, stream);            \
+    }                                                                                \
+    if (ca) return launch_tc_variant<DP, false, true>(kernel, pl, lse, stream);      \
+    return launch_tc_variant<DP, false, false>(kernel, pl, lse, stream);             \
+  } while (0)
+  if (p.D <= 64) FA_DISPATCH(64);
+  FA_DISPATCH(128);
+#undef FA_DISPATCH
+}
+
+int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse, const Problem& p,
+                cudaStream_t stream) {
+  fa::SimtParams sp;
+  sp.q = q; sp.k = k; sp.v = v; sp.o = o; sp.lse = lse;
+  sp.B = p.B; sp.H = p.H; sp.Nq = p.Nq; sp.Nkv = p.Nkv; sp.D = p.D;
+  memcpy(sp.qs, p.qs, sizeof sp.qs);
+  memcpy(sp.ks, p.ks, sizeof sp.ks);
+  memcpy(sp.vs, p.vs, sizeof sp.vs);
+  memcpy(sp.os, p.os, sizeof sp.os);
+  sp.causal = p.causal;
+  sp.scale_log2 = p.scale * 1.4426950408889634f;
+  dim3 grid((p.Nq + fa::kSimtWarps - 1) / fa::kSimtWarps, p.H, p.B);
+  const int smem = fa::kSimtWarps * p.D * static_cast<int>(sizeof(float));
+  if (p.dtype == FA_DTYPE_BF16)
+    fa::fa_fwd_simt_kernel<__nv_bfloat16><<<grid, fa::kSimtWarps * 32, smem, stream>>>(sp);
+  else
+    fa::fa_fwd_simt_kernel<__half><<<grid, fa::kSimtWarps * 32, smem, stream>>>(sp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+int check_device(int* device_out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(FA_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  }
+  static std::mutex mu;
+  static int cc_major[64];
+  static bool known[64];
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && !known[dev]) {
+      int major = 0;
+      FA_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+      cc_major[dev] = major;
+      known[dev] = true;
+    }
+  }
+  if (dev < 64 && cc_major[dev] != 10)
+    return fail(FA_ERR_NO_DEVICE, "the current device is not sm_100 (compute capability 10.x)");
+  *device_out = dev;
+  return FA_OK;
+}
+
+int resolve_kernel(const Problem& p, const void* q, const void* k, const void* v, const void* o,
+                   int* kernel_out) {
+  int kernel = choose_kernel_shape(p);
+  if (kernel != FA_KERNEL_SIMT && q != nullptr &&
+      !(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o)))
+    kernel = FA_KERNEL_SIMT;
+  const int forced = g_forced_kernel.load();
+  if (forced != FA_KERNEL_AUTO) {
+    if (forced != FA_KERNEL_SIMT && kernel == FA_KERNEL_SIMT)
+      return fail(FA_ERR_UNSUPPORTED,
+                  "forced tensor-core kernel cannot serve this problem (needs D % 8 == 0, D <= 128, "
+                  "scale > 0, 16-byte aligned pointers and strides)");
+    kernel = forced;
+  }
+  *kernel_out = kernel;
+  return FA_OK;
+}
+
+int run_device(const void* q, const void* k, const void* v, void* o, float* lse, Problem& p,
+               cudaStream_t stream) {
+  int dev;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  int kernel;
+  if ((rc = resolve_kernel(p, q, k, v, o, &kernel))) return rc;
+  if (kernel == FA_KERNEL_SIMT) return launch_simt(q, k, v, o, lse, p, stream);
+  Plan pl;
+  if ((rc = g_plans.get(q, k, v, o, p, dev, &pl))) return rc;
+  pl.p.causal = p.causal;
+  pl.p.scale = p.scale;
+  return launch_tc(kernel, pl, lse, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer path: per-device workspace + three streams
+// ---------------------------------------------------------------------------------------------
+struct HostWs {
+  bool init = false;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  void *dq = nullptr, *dk = nullptr, *dv = nullptr, *dout = nullptr;
+  float* dlse = nullptr;
+  size_t cap_q = 0, cap_kv = 0, cap_lse = 0;
+  std::vector<cudaEvent_t> ev_in, ev_run;
+};
+std::mutex g_ws_mu;
+HostWs g_ws[64];
+
+int ws_release(HostWs& w) {
+  if (w.dq) cudaFree(w.dq);
+  if (w.dk) cudaFree(w.dk);
+  if (w.dv) cudaFree(w.dv);
+  if (w.dout) cudaFree(w.dout);
+  if (w.dlse) cudaFree(w.dlse);
+  for (auto e : w.ev_in) cudaEventDestroy(e);
+  for (auto e : w.ev_run) cudaEventDestroy(e);
+  if (w.s_in) cudaStreamDestroy(w.s_in);
+  if (w.s_run) cudaStreamDestroy(w.s_run);
+  if (w.s_out) cudaStreamDestroy(w.s_out);
+  w = HostWs();
+  return FA_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported C ABI
+// =================================================================================================
+extern "C" {
+
+int fa_abi_version(void) { return FA_ABI_VERSION; }
+
+const char* fa_last_error(void) { return g_err.c_str(); }
+
+uint64_t fa_launch_count(void) { return g_launches.load(); }
+
+int fa_set_kernel(int kernel) {
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS) return -FA_ERR_INVALID_ARG;
+  return g_forced_kernel.exchange(kernel);
+}
+
+int fa_select_kernel(int B, int H, int Nq, int Nkv, int D, const int64_t q_strides[4],
+                     const int64_t k_strides[4], const int64_t v_strides[4],
+                     const int64_t o_strides[4], int dtype, int causal, float scale) {
+  Problem p{};
+  p.B = B; p.H = H; p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype; p.causal = causal;
+  p.scale = scale;
+  int rc = validate(p, q_strides, k_strides, v_strides, o_strides);
+  if (rc) return -rc;
+  int kernel;
+  if ((rc = resolve_kernel(p, nullptr, nullptr, nullptr, nullptr, &kernel))) return -rc;
+  return kernel;
+}
+
+int fa_fwd_sm100(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H,
+                 int Nq, int Nkv, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                 const int64_t v_strides[4], const int64_t o_strides[4], int dtype, int causal,
+                 float scale, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "q, k, v and o must not be null");
+  Problem p{};
+  p.B = B; p.H = H; p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype; p.causal = causal;
+  p.scale = scale;
+  int rc = validate(p, q_strides, k_strides, v_strides, o_strides);
+  if (rc) return rc;
+  return run_device(q, k, v, o, lse, p, static_cast<cudaStream_t>(stream));
+}
+
+int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                      int H, int Nq, int Nkv, int D, int dtype, int causal, float scale) {
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "q, k, v and o must not be null");
+  Problem chk{};
+  chk.B = B; chk.H = H; chk.Nq = Nq; chk.Nkv = Nkv; chk.D = D; chk.dtype = dtype;
+  chk.causal = causal; chk.scale = scale;
+  const int64_t qs[4] = {int64_t(H) * Nq * D, int64_t(Nq) * D, D, 1};
+  const int64_t ks[4] = {int64_t(H) * Nkv * D, int64_t(Nkv) * D, D, 1};
+  int rc = validate(chk, qs, ks, ks, qs);
+  if (rc) return rc;
+  int dev;
+  if ((rc = check_device(&dev))) return rc;
+  if (dev >= 64) return fail(FA_ERR_UNSUPPORTED, "device ordinal >= 64");
+
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  HostWs& w = g_ws[dev];
+  if (!w.init) {
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    w.init = true;
+  }
+  const size_t heads = size_t(B) * H;
+  const size_t q_head = size_t(Nq) * D * 2, kv_head = size_t(Nkv) * D * 2;
+  const size_t bytes_q = heads * q_head, bytes_kv = heads * kv_head;
+  const size_t bytes_lse = heads * Nq * sizeof(float);
+  if (w.cap_q < bytes_q) {
+    if (w.dq) cudaFree(w.dq);
+    if (w.dout) cudaFree(w.dout);
+    w.dq = w.dout = nullptr; w.cap_q = 0;
+    FA_CUDA_TRY(cudaMalloc(&w.dq, bytes_q));
+    FA_CUDA_TRY(cudaMalloc(&w.dout, bytes_q));
+    w.cap_q = bytes_q;
+  }
+  if (w.cap_kv < bytes_kv) {
+    if (w.dk) cudaFree(w.dk);
+    if (w.dv) cudaFree(w.dv);
+    w.dk = w.dv = nullptr; w.cap_kv = 0;
+    FA_CUDA_TRY(cudaMalloc(&w.dk, bytes_kv));
+    FA_CUDA_TRY(cudaMalloc(&w.dv, bytes_kv));
+    w.cap_kv = bytes_kv;
+  }
+  if (lse != nullptr && w.cap_lse < bytes_lse) {
+    if (w.dlse) cudaFree(w.dlse);
+    w.dlse = nullptr; w.cap_lse = 0;
+    FA_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w.dlse), bytes_lse));
+    w.cap_lse = bytes_lse;
+  }
+
+  // Chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D].
+  // Aim for >= 8 chunks of >= 4 MiB of input each so copies and kernels overlap.
+  size_t per_head = q_head + 2 * kv_head;
+  size_t hg = (size_t(4) << 20) / per_head;
+  if (hg < 1) hg = 1;
+  if (hg > (heads + 7) / 8) hg = (heads + 7) / 8;
+  if (hg < 1) hg = 1;
+  const size_t n_chunks = (heads + hg - 1) / hg;
+  while (w.ev_in.size() < n_chunks) {
+    cudaEvent_t e1, e2;
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    w.ev_in.push_back(e1);
+    w.ev_run.push_back(e2);
+  }
+
+  const char* hq = static_cast<const char*>(q);
+  const char* hk = static_cast<const char*>(k);
+  const char* hv = static_cast<const char*>(v);
+  char* ho = static_cast<char*>(o);
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t h0 = c * hg;
+    const size_t nh = (h0 + hg <= heads) ? hg : heads - h0;
+    char* dq = static_cast<char*>(w.dq) + h0 * q_head;
+    char* dk = static_cast<char*>(w.dk) + h0 * kv_head;
+    char* dv = static_cast<char*>(w.dv) + h0 * kv_head;
+    char* dout = static_cast<char*>(w.dout) + h0 * q_head;
+    FA_CUDA_TRY(cudaMemcpyAsync(dq, hq + h0 * q_head, nh * q_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(dk, hk + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(dv, hv + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaEventRecord(w.ev_in[c], w.s_in));
+    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_run, w.ev_in[c], 0));
+    // the chunk is a [1, nh, N, D] problem
+    Problem p{};
+    p.B = 1; p.H = static_cast<int>(nh); p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype;
+    p.causal = causal; p.scale = scale;
+    const int64_t cqs[4] = {int64_t(nh) * Nq * D, int64_t(Nq) * D, D, 1};
+    const int64_t cks[4] = {int64_t(nh) * Nkv * D, int64_t(Nkv) * D, D, 1};
+    if ((rc = validate(p, cqs, cks, cks, cqs))) return rc;
+    float* dl = (lse != nullptr) ? w.dlse + h0 * Nq : nullptr;
+    if ((rc = run_device(dq, dk, dv, dout, dl, p, w.s_run))) return rc;
+    FA_CUDA_TRY(cudaEventRecord(w.ev_run[c], w.s_run));
+    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_out, w.ev_run[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(ho + h0 * q_head, dout, nh * q_head, cudaMemcpyDeviceToHost, w.s_out));
+    if (lse != nullptr)
+      FA_CUDA_TRY(cudaMemcpyAsync(lse + h0 * Nq, dl, nh * Nq * sizeof(float),
+                                  cudaMemcpyDeviceToHost, w.s_out));
+  }
+  FA_CUDA_TRY(cudaStreamSynchronize(w.s_out));
+  return FA_OK;
+}
+
+int fa_host_workspace_release(void) {
+  int dev;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  if (dev >= 64) return FA_OK;
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  return ws_release(g_ws[dev]);
+}
+
+int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mode, uint32_t lbo,
+                     uint32_t sbo, void* stream) {
+  if (a == nullptr || b == nullptr || out == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "a, b and out must not be null");
+  if (mode < 0 || mode > 3) return fail(FA_ERR_INVALID_ARG, "mode must be 0..3");
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
+    return fail(FA_ERR_INVALID_ARG, "dtype must be FA_DTYPE_F16 or FA_DTYPE_BF16");
+  int dev;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  if (lbo == 0 && sbo == 0) { lbo = 16384; sbo = 1024; }
+  const int64_t st[4] = {128 * 128, 128 * 128, 128, 1};
+  CUtensorMap ma, mb;
+  if ((rc = make_map(&ma, a, 1, 1, 128, 128, st, dtype, 128))) return rc;
+  if ((rc = make_map(&mb, b, 1, 1, 128, 128, st, dtype, 128))) return rc;
+  const int smem = 65536 + 128 + 1024;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == FA_DTYPE_BF16) {
+    if ((rc = set_smem(fa::umma_probe_kernel<true>, smem))) return rc;
+    fa::umma_probe_kernel<true><<<1, 128, smem, s>>>(ma, mb, static_cast<const uint16_t*>(a), out,
+                                                     mode, lbo, sbo);
+  } else {
+    if ((rc = set_smem(fa::umma_probe_kernel<false>, smem))) return rc;
+    fa::umma_probe_kernel<false><<<1, 128, smem, s>>>(ma, mb, static_cast<const uint16_t*>(a), out,
+                                                      mode, lbo, sbo);
+  }
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+}  // extern "C"

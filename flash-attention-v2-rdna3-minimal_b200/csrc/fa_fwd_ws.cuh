@@ -1,0 +1,390 @@
+// Warp-specialised tcgen05 forward kernel ("ws"): the fast path.
+//
+// One CTA = one (batch, head, 256-row Q block) = two 128-row Q tiles that ping-pong on the tensor
+// cores: while the softmax warpgroup of tile 0 works on S0(j) in registers, the tensor cores
+// compute S1(j) / O1 += P1 V, and vice versa.  16 warps:
+//
+//   warps  0- 3  softmax warpgroup for Q tile 0   (one thread = one query row = one TMEM lane)
+//   warps  4- 7  softmax warpgroup for Q tile 1
+//   warps  8-11  correction warpgroup: rescales the O accumulators in TMEM when a row max moved,
+//                and runs the epilogue (O / l -> 16 bit -> smem -> TMA store)
+//   warp  12     MMA issuer (one thread issues every tcgen05.mma)
+//   warp  13     TMA producer (Q once, then the K/V ring)
+//   warps 14-15  idle (they only donate their registers)
+//
+// TMEM (512 columns x 128 lanes x 32 bit):  S0 [0,128)  S1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
+// P (16-bit) overwrites the first 64 columns of its S tile and feeds the PV MMA from TMEM (TS form).
+//
+// MMA issue order (K/V ring order is K0 V0 K1 V1 ...):
+//   S0(0) S1(0) | PV0(0) S0(1) PV1(0) S1(1) | PV0(1) S0(2) PV1(1) S1(2) | ...
+//
+// Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 / kernel_bf16.cu:329-576 and the
+// device GEMM helpers (:115-302); see fa_fwd_tc.cuh for the serial version of the same algorithm.
+#pragma once
+#include "fa_fwd_tc.cuh"
+
+namespace fa {
+
+template <int kDP>
+struct WsCfg {
+  static constexpr int kTileBytes = kTileM * kDP * 2;
+  static constexpr int kStages = (kDP == 128) ? 4 : 8;  // K/V ring slots (one K or one V tile each)
+  static constexpr int kQ = 0;                           // 2 Q tiles (re-used as O staging)
+  static constexpr int kKV = kQ + 2 * kTileBytes;
+  static constexpr int kBars = kKV + kStages * kTileBytes;
+  static constexpr int kNumBars = 10 + 2 * kStages;
+  static constexpr int kScale = kBars + 8 * kNumBars + 16;  // float [2][128] rescale factors
+  static constexpr int kFinal = kScale + 2 * 128 * 4;       // float [2][128] final row sums
+  static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
+};
+
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the max grew by > 2^8
+
+template <int kDP, bool kBF16, bool kCausal>
+__global__ void __launch_bounds__(512, 1)
+fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                 const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v,
+                 const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
+  using C = WsCfg<kDP>;
+  constexpr int kS = C::kStages;
+  constexpr int kDBlocks = kDP / 64;
+  constexpr int kKSteps = kDP / 16;
+  auto col_s = [](int t) -> uint32_t { return static_cast<uint32_t>(t) * 128u; };
+  auto col_o = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u; };
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t sQ = smem_u32(smem + C::kQ);
+  const uint32_t sKV = smem_u32(smem + C::kKV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kBars + 8 * C::kNumBars);
+  float* sScale = reinterpret_cast<float*>(smem + C::kScale);
+  float* sFinal = reinterpret_cast<float*>(smem + C::kFinal);
+
+  // barrier map
+  auto bar_q_full = [&](int t) { return smem_u32(&bars[t]); };          // tx, count 1
+  auto bar_s_full = [&](int t) { return smem_u32(&bars[2 + t]); };      // tcgen05.commit
+  auto bar_scale = [&](int t) { return smem_u32(&bars[4 + t]); };       // 128 softmax threads
+  auto bar_po = [&](int t) { return smem_u32(&bars[6 + t]); };          // 128 softmax + 128 correction
+  auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[10 + s]); };    // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[10 + kS + s]); };  // tcgen05.commit
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int pair = kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // longest blocks first
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row0 = pair * 2 * kTileM;
+
+  // per-tile KV trip counts
+  const int n_kv_total = (p.Nkv + kTileN - 1) / kTileN;
+  int n_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = row0 + t * kTileM;
+    int n = (r0 < p.Nq) ? n_kv_total : 0;
+    if (kCausal) n = min(n, r0 / kTileN + 1);
+    n_t[t] = n;
+  }
+  const int n_max = max(n_t[0], n_t[1]);
+
+  if (warp == 12 && lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_q_full(t), 1);
+      mbar_init(bar_s_full(t), 1);
+      mbar_init(bar_scale(t), 128);
+      mbar_init(bar_po(t), 256);
+      mbar_init(bar_o_final(t), 1);
+    }
+#pragma unroll
+    for (int s = 0; s < kS; ++s) {
+      mbar_init(bar_kv_full(s), 1);
+      mbar_init(bar_kv_empty(s), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp == 12) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float c = p.scale_log2;
+
+  if (warp >= 12) {
+    // =========================================================================================
+    // warpgroup 3: MMA issuer (warp 12), TMA producer (warp 13)
+    // =========================================================================================
+    setmaxnreg_dec<64>();
+    if (warp == 13) {
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (n_t[t] > 0) {
+            mbar_arrive_expect_tx(bar_q_full(t), C::kTileBytes);
+#pragma unroll
+            for (int db = 0; db < kDBlocks; ++db)
+              tma_load_4d(sQ + t * C::kTileBytes + db * 16384, &tmap_q, bar_q_full(t), db * 64,
+                          row0 + t * kTileM, h, b);
+          }
+        }
+#pragma unroll 1
+        for (int idx = 0; idx < 2 * n_max; ++idx) {  // ring order K0 V0 K1 V1 ...
+          const int slot = idx % kS;
+          const uint32_t use = idx / kS;
+          mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
+          mbar_arrive_expect_tx(bar_kv_full(slot), C::kTileBytes);
+          const CUtensorMap* map = (idx & 1) ? &tmap_v : &tmap_k;
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db)
+            tma_load_4d(sKV + slot * C::kTileBytes + db * 16384, map, bar_kv_full(slot), db * 64,
+                        (idx >> 1) * kTileN, h, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 12) {
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
+        constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);
+
+        auto wait_kv = [&](int idx) {
+          mbar_wait(bar_kv_full(idx % kS), (idx / kS) & 1, 30);
+          tc_fence_after();
+        };
+        auto release_kv = [&](int idx) { tc_commit(bar_kv_empty(idx % kS)); };
+        auto issue_s = [&](int t, int j) {  // S_t = Q_t K_j^T
+          const uint32_t kbase = sKV + ((2 * j) % kS) * C::kTileBytes;
+          const uint32_t qbase = sQ + t * C::kTileBytes;
+#pragma unroll
+          for (int k = 0; k < kKSteps; ++k) {
+            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+            umma_ss(tmem + col_s(t), make_smem_desc_sw128(qbase + off, 16, 1024),
+                    make_smem_desc_sw128(kbase + off, 16, 1024), idesc_s, k > 0);
+          }
+          tc_commit(bar_s_full(t));
+        };
+        auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
+          const uint32_t vbase = sKV + ((2 * j + 1) % kS) * C::kTileBytes;
+          mbar_wait(bar_po(t), j & 1, 31 + t);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTileN / 16; ++k) {
+            umma_ts(tmem + col_o(t), tmem + col_s(t) + k * 8,
+                    make_smem_desc_sw128(vbase + k * 2048, 16384, 1024), idesc_o,
+                    (j > 0) || (k > 0));
+          }
+          if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
+        };
+
+        if (n_max > 0) {
+          wait_kv(0);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (n_t[t] > 0) {
+              mbar_wait(bar_q_full(t), 0, 33);
+              tc_fence_after();
+              issue_s(t, 0);
+            }
+          }
+          release_kv(0);
+        }
+#pragma unroll 1
+        for (int j = 0; j < n_max; ++j) {
+          const int nx = j + 1;
+          wait_kv(2 * j + 1);
+          if (j < n_t[0]) issue_pv(0, j);
+          if (nx < n_max) wait_kv(2 * nx);
+          if (nx < n_t[0]) issue_s(0, nx);
+          if (j < n_t[1]) issue_pv(1, j);
+          release_kv(2 * j + 1);
+          if (nx < n_t[1]) issue_s(1, nx);
+          if (nx < n_max) release_kv(2 * nx);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp < 8) {
+    // =========================================================================================
+    // softmax warpgroups
+    // =========================================================================================
+    setmaxnreg_inc<184>();
+    const int t = warp >> 2;
+    const int r = tid & 127;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_base + col_s(t);
+    const int tile_row0 = row0 + t * kTileM;
+    const int diag_j = tile_row0 / kTileN;
+    const int n = n_t[t];
+
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(bar_s_full(t), j & 1, 40 + t);
+      tc_fence_after();
+      float s[kTileN];
+#pragma unroll
+      for (int cidx = 0; cidx < 4; ++cidx)
+        tmem_ld_x32(tS + cidx * 32, reinterpret_cast<uint32_t*>(s) + cidx * 32);
+      tmem_wait_ld();
+
+      const int col0 = j * kTileN;
+      const bool tail = (col0 + kTileN > p.Nkv);
+      const bool diag = kCausal && (j == diag_j);
+      if (tail || diag) {
+        const int valid = tail ? (p.Nkv - col0) : kTileN;
+        const int lim = diag ? min(valid, r + 1) : valid;  // columns [0, lim) are visible
+#pragma unroll
+        for (int i = 0; i < kTileN; ++i)
+          if (i >= lim) s[i] = -INFINITY;
+      }
+
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int i = 4; i < kTileN; i += 4) {
+        mx0 = fmaxf(mx0, s[i]);
+        mx1 = fmaxf(mx1, s[i + 1]);
+        mx2 = fmaxf(mx2, s[i + 2]);
+        mx3 = fmaxf(mx3, s[i + 3]);
+      }
+      const float m_cand = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_run);
+      float alpha = 1.f;
+      if ((m_cand - m_run) * c > kRescaleThreshold) {  // also true for the first tile (m_run = -inf)
+        alpha = ex2_approx((m_run - m_cand) * c);
+        m_run = m_cand;
+      }
+      if (j > 0) {
+        sScale[t * 128 + r] = alpha;
+        mbar_arrive(bar_scale(t));
+      }
+      const float mc = m_run * c;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kTileN; i += 4) {
+        s[i] = ex2_approx(fmaf(s[i], c, -mc));
+        s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
+        s[i + 2] = ex2_approx(fmaf(s[i + 2], c, -mc));
+        s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
+        sum0 += s[i];
+        sum1 += s[i + 1];
+        sum2 += s[i + 2];
+        sum3 += s[i + 3];
+      }
+      l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          pk[i] = pack2<kBF16>(s[hlf * 64 + 2 * i], s[hlf * 64 + 2 * i + 1]);
+        tmem_st_x32(tS + hlf * 32, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_po(t));
+    }
+
+    if (n > 0) {
+      sFinal[t * 128 + r] = l_run;
+      mbar_arrive(bar_scale(t));
+      const int row = tile_row0 + r;
+      if (p.lse != nullptr && row < p.Nq)
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + row] = m_run * c + log2f(l_run);
+    }
+  } else {
+    // =========================================================================================
+    // correction warpgroup (warps 8-11)
+    // =========================================================================================
+    setmaxnreg_dec<80>();
+    const int r = tid & 127;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+
+#pragma unroll 1
+    for (int j = 0; j < n_max; ++j) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (j < n_t[t]) {
+          if (j > 0) {
+            mbar_wait(bar_scale(t), (j - 1) & 1, 50 + t);
+            const float a = sScale[t * 128 + r];
+            if (__any_sync(0xffffffffu, a != 1.f)) {
+              tc_fence_after();
+#pragma unroll
+              for (int cidx = 0; cidx < kDP / 32; ++cidx) {
+                uint32_t o[32];
+                tmem_ld_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a);
+                tmem_st_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
+              }
+              tmem_wait_st();
+              tc_fence_before();
+            }
+          }
+          mbar_arrive(bar_po(t));
+        }
+      }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (n_t[t] > 0) {
+        mbar_wait(bar_scale(t), (n_t[t] - 1) & 1, 52 + t);
+        const float inv_l = 1.f / sFinal[t * 128 + r];
+        mbar_wait(bar_o_final(t), 0, 54 + t);
+        tc_fence_after();
+        uint8_t* stage = smem + C::kQ + t * C::kTileBytes;
+#pragma unroll
+        for (int cidx = 0; cidx < kDP / 32; ++cidx) {
+          uint32_t o[32];
+          tmem_ld_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 val;
+            val.x = pack2<kBF16>(__uint_as_float(o[ch * 8 + 0]) * inv_l, __uint_as_float(o[ch * 8 + 1]) * inv_l);
+            val.y = pack2<kBF16>(__uint_as_float(o[ch * 8 + 2]) * inv_l, __uint_as_float(o[ch * 8 + 3]) * inv_l);
+            val.z = pack2<kBF16>(__uint_as_float(o[ch * 8 + 4]) * inv_l, __uint_as_float(o[ch * 8 + 5]) * inv_l);
+            val.w = pack2<kBF16>(__uint_as_float(o[ch * 8 + 6]) * inv_l, __uint_as_float(o[ch * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, cidx * 32 + ch * 8)) = val;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (r == 0) {
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db)
+            tma_store_4d(&tmap_o, sQ + t * C::kTileBytes + db * 16384, db * 64, row0 + t * kTileM,
+                         h, b);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+    }
+    if (r == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fa

@@ -1,0 +1,193 @@
+"""Drop-in for the forward path of /root/reference/rocwmma_fattn/FlashAttn.py.
+
+Same entry point and calling convention as the reference::
+
+    from rocwmma_fattn.FlashAttn import FlashAttentionFunction
+    o = FlashAttentionFunction.apply(q, k, v, mask, causal, scale, BNHD_fmt)
+
+* ``q`` is ``[B,H,N,D]`` (or ``[B,N,H,D]`` with ``BNHD_fmt=True``), ``k``/``v`` likewise with ``Nkv``;
+  the result has the shape, dtype and memory layout of ``q`` (reference: FlashAttn.py:49-76).
+* ``mask`` is accepted and ignored, exactly as in the reference (FlashAttn.py:49,74).
+* ``causal=None`` means False; the mask is top-left aligned (``col > row`` masked,
+  kernel_fp16.cu:396-412), i.e. ``F.scaled_dot_product_attention(is_causal=True)``.
+* ``scale`` defaults to ``D ** -0.5`` (FlashAttn.py:63-64).
+* inputs that are neither fp16 nor bf16 are computed in bf16 (host.cpp:41-44).
+
+Underneath, instead of the JIT-hipified rocWMMA extension, this calls the C-ABI library
+``lib/libfa_fwd_sm100.so`` (include/fa_fwd_sm100.h) through ctypes with raw device pointers and
+strides.  Tile sizes (the reference's Br/Bc, FlashAttn.py:56-67) are internal to the kernels.  There
+is no CPU fallback: CPU tensors raise, and a missing library fails the import.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi
+
+__all__ = [
+    "FlashAttentionFunction",
+    "flash_attn_forward",
+    "flash_attn_forward_host",
+    "flash_attn_wmma",
+]
+
+_TMA_D_ALIGN = 8  # head dim multiple of 16 bytes for the tensor-core (TMA) kernels
+_TC_MAX_D = 128
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float16:
+        return _capi.FA_DTYPE_F16
+    if dt == torch.bfloat16:
+        return _capi.FA_DTYPE_BF16
+    raise TypeError(f"unsupported dtype {dt}")
+
+
+def _logical_strides(t: torch.Tensor, bnhd: bool):
+    """Element strides in logical (b, h, n, d) order; the identity the reference's kernels apply
+    for ``permute_NH`` (kernel_fp16.cu:324-333, checked by test_arrange.py:23-30)."""
+    s = t.stride()
+    return (s[0], s[2], s[1], s[3]) if bnhd else (s[0], s[1], s[2], s[3])
+
+
+def _logical_shape(t: torch.Tensor, bnhd: bool):
+    sh = t.shape
+    return (sh[0], sh[2], sh[1], sh[3]) if bnhd else (sh[0], sh[1], sh[2], sh[3])
+
+
+def _prepare(t: torch.Tensor, d_pad: int) -> torch.Tensor:
+    if d_pad:
+        t = torch.nn.functional.pad(t, (0, d_pad))  # reference pads D too (kernel_fp16.cu:763-779)
+    if t.stride(-1) != 1:
+        t = t.contiguous()  # kernel_fp16.cu:780-787
+    return t
+
+
+def _forward(q, k, v, causal, scale, bnhd, want_lse):
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError("q, k, v must be 4-D: [B,H,N,D] or [B,N,H,D] (BNHD_fmt=True)")
+    if not q.is_cuda:
+        raise RuntimeError(
+            "rocwmma_fattn (B200 build) runs on CUDA tensors only; there is no CPU fallback"
+        )
+    if k.device != q.device or v.device != q.device:
+        raise ValueError("q, k, v must be on the same device")
+    if q.dtype not in (torch.float16, torch.bfloat16):
+        # reference: host.cpp:41-44 casts anything else to bf16 and returns bf16
+        q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("q, k, v must share one dtype")
+
+    B, H, Nq, D = _logical_shape(q, bnhd)
+    Bk, Hk, Nkv, Dk = _logical_shape(k, bnhd)
+    if (Bk, Hk, Dk) != (B, H, D) or _logical_shape(v, bnhd) != (Bk, Hk, Nkv, Dk):
+        raise ValueError(
+            f"shape mismatch: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}"
+        )
+    if min(B, H, Nq, Nkv, D) < 1:
+        raise ValueError("empty tensors are not supported (every dimension must be >= 1)")
+    if scale is None:
+        scale = D ** -0.5
+    causal = bool(causal)
+
+    # head dims that are not a multiple of 8 cannot be addressed by TMA: zero-pad them (zeros change
+    # neither q.k nor the first D columns of p.v); D > 128 goes to the generic kernel unpadded.
+    d_pad = (-D) % _TMA_D_ALIGN if D < _TC_MAX_D else 0
+    qp, kp, vp = _prepare(q, d_pad), _prepare(k, d_pad), _prepare(v, d_pad)
+    o_full = torch.empty_like(qp)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if want_lse else None
+
+    with torch.cuda.device(q.device):
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        rc = _capi.lib.fa_fwd_sm100(
+            qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), o_full.data_ptr(),
+            lse.data_ptr() if lse is not None else None,
+            B, H, Nq, Nkv, D + d_pad,
+            _capi.strides4(_logical_strides(qp, bnhd)), _capi.strides4(_logical_strides(kp, bnhd)),
+            _capi.strides4(_logical_strides(vp, bnhd)), _capi.strides4(_logical_strides(o_full, bnhd)),
+            _dtype_code(qp.dtype), int(causal), float(scale), stream,
+        )
+    _capi.check(rc, "fa_fwd_sm100")
+    o = o_full[..., :D] if d_pad else o_full
+    return o, lse, (qp, kp, vp, o_full), (causal, float(scale), Nq, Nkv, D, bnhd)
+
+
+def flash_attn_forward(q, k, v, causal=False, scale=None, BNHD_fmt=False, return_lse=False):
+    """Functional form of the forward.  With ``return_lse`` also returns the base-2 log-sum-exp of
+    the scaled scores, fp32 ``[B,H,Nq]`` (what the reference stores in ``L``,
+    kernel_fp16.cu:541-542)."""
+    o, lse, _, _ = _forward(q, k, v, causal, scale, BNHD_fmt, return_lse)
+    return (o, lse) if return_lse else o
+
+
+def flash_attn_forward_host(q, k, v, causal=False, scale=None, out=None, return_lse=False):
+    """Forward on HOST tensors (contiguous ``[B,H,N,D]``, ideally pinned): the C-ABI stages the
+    inputs to the current CUDA device, runs the same kernels and copies the result back, overlapping
+    the copies with compute.  Returns a host tensor (``out`` if given).  This is the end-to-end
+    path ``bench.py`` reports as ``e2e``."""
+    for t in (q, k, v):
+        if t.is_cuda or t.dim() != 4 or not t.is_contiguous():
+            raise ValueError("flash_attn_forward_host expects contiguous 4-D host tensors")
+    if q.dtype not in (torch.float16, torch.bfloat16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("q, k, v must be fp16 or bf16 and share one dtype")
+    B, H, Nq, D = q.shape
+    Nkv = k.shape[2]
+    if k.shape != (B, H, Nkv, D) or v.shape != k.shape:
+        raise ValueError("shape mismatch between q, k, v")
+    if scale is None:
+        scale = D ** -0.5
+    if out is None:
+        out = torch.empty_like(q, pin_memory=q.is_pinned())
+    elif out.shape != q.shape or out.dtype != q.dtype or out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous host tensor shaped and typed like q")
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, pin_memory=q.is_pinned()) if return_lse else None
+    rc = _capi.lib.fa_fwd_sm100_host(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+        lse.data_ptr() if lse is not None else None,
+        B, H, Nq, Nkv, D, _dtype_code(q.dtype), int(bool(causal)), float(scale),
+    )
+    _capi.check(rc, "fa_fwd_sm100_host")
+    return (out, lse) if return_lse else out
+
+
+class _NativeModule:
+    """Stand-in for the reference's pybind module object ``flash_attn_wmma`` (FlashAttn.py:23,
+    host.cpp:60-64): ``forward(q,k,v,Br,Bc,causal,scale,permute_NH)`` returns the same six tensors
+    ``[O_view, q_pad, k_pad, v_pad, O_pad, L]`` (kernel_fp16.cu:875).  Br/Bc are accepted for
+    signature compatibility and ignored: tile sizes are internal to the sm_100a kernels."""
+
+    @staticmethod
+    def forward(q, k, v, Br, Bc, causal, scale, permute_NH):
+        o, lse, (qp, kp, vp, o_full), _ = _forward(q, k, v, causal, scale, permute_NH, True)
+        return [o, qp, kp, vp, o_full, lse]
+
+    @staticmethod
+    def backward(*args, **kwargs):
+        raise NotImplementedError(
+            "the B200 build implements the forward path only (SURVEY.md section 8f ranks the "
+            "backward kernel as the next component); use the saved (q, k, v, o, L) with your own "
+            "backward or torch SDPA for training"
+        )
+
+
+flash_attn_wmma = _NativeModule()
+
+
+class FlashAttentionFunction(torch.autograd.Function):
+    """Reference: /root/reference/rocwmma_fattn/FlashAttn.py:45-92."""
+
+    @staticmethod
+    @torch.no_grad()
+    def forward(ctx, q, k, v, mask=None, causal=None, scale=None, BNHD_fmt=False, *args, **kwargs):
+        need_grad = q.requires_grad or k.requires_grad or v.requires_grad
+        o, lse, saved, meta = _forward(q, k, v, causal, scale, BNHD_fmt, need_grad)
+        if need_grad:
+            causal_, scale_, N, Nkv, D, bnhd = meta
+            ctx.args = (causal_, scale_, mask, N, Nkv, D, bnhd)
+            ctx.save_for_backward(*saved, lse)
+        return o
+
+    @staticmethod
+    @torch.no_grad()
+    def backward(ctx, do):
+        return flash_attn_wmma.backward(ctx, do)

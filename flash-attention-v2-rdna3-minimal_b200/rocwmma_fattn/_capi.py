@@ -1,0 +1,126 @@
+"""ctypes binding of ``include/fa_fwd_sm100.h`` (the C-ABI that replaces the reference's pybind
+module ``flash_attn_wmma``, /root/reference/rocwmma_fattn/host.cpp:60-64).
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc, and if that fails
+the import raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import importlib.util
+import os
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
+
+FA_ABI_VERSION = 1
+FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
+FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0, 1, 2, 3, 4
+FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS = 0, 1, 2, 3, 4
+KERNEL_NAMES = {
+    FA_KERNEL_AUTO: "auto",
+    FA_KERNEL_SIMT: "simt",
+    FA_KERNEL_TC1: "tc1",
+    FA_KERNEL_TC1_PSMEM: "tc1_psmem",
+    FA_KERNEL_WS: "ws",
+}
+
+# every symbol include/fa_fwd_sm100.h declares
+EXPORTED_SYMBOLS = (
+    "fa_fwd_sm100",
+    "fa_fwd_sm100_host",
+    "fa_host_workspace_release",
+    "fa_last_error",
+    "fa_abi_version",
+    "fa_select_kernel",
+    "fa_set_kernel",
+    "fa_launch_count",
+    "fa_umma_selftest",
+)
+
+_I64x4 = ctypes.c_int64 * 4
+
+
+def _load_build_module():
+    spec = importlib.util.spec_from_file_location("_fa_build", os.path.join(_PKG_ROOT, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _open() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        # same contract as the reference (build at import, FlashAttn.py:23-41), but ahead-of-time
+        # builds are preferred: `python __graft_entry__.py` / `python build.py`
+        _load_build_module().build()
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    p64 = ctypes.POINTER(ctypes.c_int64)
+    lib.fa_fwd_sm100.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, p64, p64, p64, p64, i, i, f, vp]
+    lib.fa_fwd_sm100.restype = i
+    lib.fa_fwd_sm100_host.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f]
+    lib.fa_fwd_sm100_host.restype = i
+    lib.fa_host_workspace_release.argtypes = []
+    lib.fa_host_workspace_release.restype = i
+    lib.fa_last_error.argtypes = []
+    lib.fa_last_error.restype = ctypes.c_char_p
+    lib.fa_abi_version.argtypes = []
+    lib.fa_abi_version.restype = i
+    lib.fa_select_kernel.argtypes = [i, i, i, i, i, p64, p64, p64, p64, i, i, f]
+    lib.fa_select_kernel.restype = i
+    lib.fa_set_kernel.argtypes = [i]
+    lib.fa_set_kernel.restype = i
+    lib.fa_launch_count.argtypes = []
+    lib.fa_launch_count.restype = ctypes.c_uint64
+    lib.fa_umma_selftest.argtypes = [vp, vp, vp, i, i, ctypes.c_uint32, ctypes.c_uint32, vp]
+    lib.fa_umma_selftest.restype = i
+    if lib.fa_abi_version() != FA_ABI_VERSION:
+        raise RuntimeError(
+            f"{LIB_PATH}: ABI version {lib.fa_abi_version()} != expected {FA_ABI_VERSION}; rebuild"
+        )
+    return lib
+
+
+lib = _open()
+
+
+class FlashAttnError(RuntimeError):
+    """Raised when the C-ABI returns a non-zero code (the reference only printf'd,
+    /root/reference/rocwmma_fattn/kernel_fp16.cu:854-863)."""
+
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib.fa_last_error().decode("utf-8", "replace")
+        super().__init__(f"{where} failed with code {code}: {msg}")
+
+
+def check(code: int, where: str) -> None:
+    if code != FA_OK:
+        raise FlashAttnError(code, where)
+
+
+def strides4(st) -> "ctypes.Array":
+    return _I64x4(int(st[0]), int(st[1]), int(st[2]), int(st[3]))
+
+
+def last_error() -> str:
+    return lib.fa_last_error().decode("utf-8", "replace")
+
+
+def launch_count() -> int:
+    return int(lib.fa_launch_count())
+
+
+def set_kernel(kernel: int) -> int:
+    prev = lib.fa_set_kernel(int(kernel))
+    if prev < 0:
+        raise ValueError(f"unknown kernel selector {kernel}")
+    return prev
+
+
+def select_kernel(B, H, Nq, Nkv, D, qs, ks, vs, os_, dtype, causal, scale) -> int:
+    r = lib.fa_select_kernel(B, H, Nq, Nkv, D, strides4(qs), strides4(ks), strides4(vs),
+                             strides4(os_), dtype, int(bool(causal)), float(scale))
+    if r < 0:
+        raise FlashAttnError(-r, "fa_select_kernel")
+    return r

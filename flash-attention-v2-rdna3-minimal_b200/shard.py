@@ -1,0 +1,37 @@
+"""Multi-GPU plan for the forward path: an NCCL-free batch shard.
+
+Every (batch, head, Q-tile) of the forward is independent (reference grid
+``(b, h, Tr)``, /root/reference/rocwmma_fattn/kernel_fp16.cu:803-806), so N GPUs simply take
+contiguous slices of the batch axis and run the single-GPU kernel; nothing is exchanged on the data
+path.  The only cross-rank traffic is the scalar timing / launch-count reduction bench.py does with
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+
+def shard_batch(total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous slice ``(start, count)`` of ``total`` batch elements owned by ``rank``.
+    The first ``total % world`` ranks get one extra element; counts may be 0 if world > total."""
+    if world < 1 or not (0 <= rank < world) or total < 0:
+        raise ValueError(f"bad shard request total={total} world={world} rank={rank}")
+    base, extra = divmod(total, world)
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
+def reduce_max_time(local_ms: float, dist=None, device=None) -> float:
+    """Job time = max over ranks of the device time each rank measured."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(local_ms)
+    import torch
+
+    t = torch.tensor([local_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_tflops(flops_all_ranks: float, local_ms: float, dist=None, device=None) -> float:
+    """Whole-job TFLOPS = FLOPs of all ranks / max-over-ranks time."""
+    ms = reduce_max_time(local_ms, dist, device)
+    return flops_all_ranks / (ms * 1e-3) / 1e12

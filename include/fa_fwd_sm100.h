@@ -1,0 +1,126 @@
+/*
+ * fa_fwd_sm100.h — C ABI of the B200 (sm_100a) Flash-Attention-2 forward path.
+ *
+ * This is the drop-in boundary for the forward half of the reference's native extension:
+ *
+ *   reference interface                                   replaced by
+ *   ---------------------------------------------------   ---------------------------------
+ *   rocwmma_fattn/host.cpp:30-45   forward(q,k,v,Br,Bc,   fa_fwd_sm100()
+ *        causal,scale,permute_NH)  (pybind11, dtype
+ *        dispatch fp16 / bf16)
+ *   rocwmma_fattn/kernel_fp16.cu:744-876  forward_fp16()  fa_fwd_sm100(dtype = FA_DTYPE_F16)
+ *   rocwmma_fattn/kernel_bf16.cu:802-941  forward_bf16()  fa_fwd_sm100(dtype = FA_DTYPE_BF16)
+ *   kernel_fp16.cu:854-863  printf-only launch errors     return code + fa_last_error()
+ *
+ * Differences from the reference, by design:
+ *   - plain pointers, sizes and element strides; no torch types cross this boundary;
+ *   - the caller owns every buffer (o, lse); the library allocates no tensors and makes no hidden
+ *     padded / contiguous copies: both [B,H,N,D] and [B,N,H,D] are consumed in place through the
+ *     stride arguments (the reference's `permute_NH` flag is subsumed by the strides);
+ *   - Br/Bc tile sizes are internal to the kernels;
+ *   - the launch goes to the CUDA stream the caller passes (the reference uses the legacy default
+ *     stream) and is asynchronous.
+ *
+ * All functions are thread-safe; errors are reported per thread.
+ */
+#ifndef FA_FWD_SM100_H_
+#define FA_FWD_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_ABI_VERSION 1
+
+/* element types (reference: host.cpp:32-44 dispatches on torch::kFloat16 / torch::kBFloat16) */
+#define FA_DTYPE_F16 0
+#define FA_DTYPE_BF16 1
+
+/* return codes */
+#define FA_OK 0
+#define FA_ERR_INVALID_ARG 1   /* bad shape / dtype / stride / null pointer */
+#define FA_ERR_UNSUPPORTED 2   /* valid request this build cannot serve (e.g. head dim > 1024) */
+#define FA_ERR_CUDA 3          /* a CUDA runtime / driver call failed */
+#define FA_ERR_NO_DEVICE 4     /* no sm_100 device is current */
+
+/* kernel selectors for fa_set_kernel() / fa_select_kernel() */
+#define FA_KERNEL_AUTO 0
+#define FA_KERNEL_SIMT 1       /* CUDA-core kernel, any head dim <= 1024 */
+#define FA_KERNEL_TC1 2        /* tcgen05, one 128-row Q tile per CTA, P through TMEM */
+#define FA_KERNEL_TC1_PSMEM 3  /* as TC1 but P through shared memory */
+#define FA_KERNEL_WS 4         /* tcgen05, warp-specialised, two Q tiles per CTA (the fast path) */
+
+/*
+ * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu
+ * `forward_fp16/bf16`.
+ *
+ *   q        [B,H,Nq ,D] logical; element strides q_strides[4] in the order (b,h,n,d)
+ *   k, v     [B,H,Nkv,D] logical; strides k_strides / v_strides
+ *   o        [B,H,Nq ,D] logical; strides o_strides; written by the kernel (same dtype as q)
+ *   lse      optional (may be NULL): contiguous fp32 [B,H,Nq]; receives
+ *            L = max_j(s_ij)*log2(e) + log2(sum_j exp(s_ij - max)) with s = scale * q.k, i.e. the
+ *            base-2 log-sum-exp the reference stores (kernel_fp16.cu:541-542)
+ *   dtype    FA_DTYPE_F16 or FA_DTYPE_BF16 (q, k, v, o all share it)
+ *   causal   non-zero: mask col > row (top-left aligned, kernel_fp16.cu:396-412)
+ *   scale    softmax scale (the Python layer defaults it to D**-0.5, FlashAttn.py:63-64)
+ *   stream   cudaStream_t to launch on (NULL = legacy default stream)
+ *
+ * The innermost stride (d) of every tensor must be 1.  Returns FA_OK or an error code; the launch
+ * is asynchronous with respect to the host.
+ */
+int fa_fwd_sm100(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H,
+                 int Nq, int Nkv, int D, const int64_t q_strides[4], const int64_t k_strides[4],
+                 const int64_t v_strides[4], const int64_t o_strides[4], int dtype, int causal,
+                 float scale, void* stream);
+
+/*
+ * Same computation with HOST buffers (contiguous [B,H,N,D]; pinned memory recommended).  Inputs are
+ * staged to the current device head-group by head-group on internal streams so that the
+ * host->device copy of group i+1 and the device->host copy of group i-1 overlap the kernel of
+ * group i; returns after the last output byte has landed in `o`.  This is the end-to-end path
+ * bench.py reports as `e2e`.  `lse` may be NULL.
+ */
+int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                      int H, int Nq, int Nkv, int D, int dtype, int causal, float scale);
+
+/* Release the device workspace and streams fa_fwd_sm100_host() caches for the current device. */
+int fa_host_workspace_release(void);
+
+/* Message describing the last error on the calling thread ("" if none). */
+const char* fa_last_error(void);
+
+/* FA_ABI_VERSION the library was built with. */
+int fa_abi_version(void);
+
+/*
+ * Which kernel fa_fwd_sm100() would run for this problem (one of FA_KERNEL_*, never AUTO), or a
+ * negative error code.  Pure host logic: usable without a GPU.
+ */
+int fa_select_kernel(int B, int H, int Nq, int Nkv, int D, const int64_t q_strides[4],
+                     const int64_t k_strides[4], const int64_t v_strides[4],
+                     const int64_t o_strides[4], int dtype, int causal, float scale);
+
+/* Force a kernel (FA_KERNEL_*) for subsequent calls in this process; FA_KERNEL_AUTO restores the
+ * heuristic.  Test / benchmarking hook.  Returns the previous setting. */
+int fa_set_kernel(int kernel);
+
+/* Number of kernel launches issued by this library in this process (all threads). */
+uint64_t fa_launch_count(void);
+
+/*
+ * UMMA / TMA / TMEM self-test: computes one 128x128x128 product through the same operand paths the
+ * attention kernels use (mode 0: A.B^T both K-major; 1: A.B with B MN-major; 2: A from TMEM;
+ * 3: A written to smem by threads).  a, b: device [128,128] 16-bit row-major; out: device
+ * [128,128] fp32.  lbo/sbo: B-descriptor byte offsets for modes 1-3 (0,0 = the values the kernels
+ * use).  Counterpart of the reference's gemm_test/ micro-kernels.
+ */
+int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mode, uint32_t lbo,
+                     uint32_t sbo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FA_FWD_SM100_H_ */

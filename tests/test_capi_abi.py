@@ -1,0 +1,128 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/fa_fwd_sm100.h declares, validates arguments, and fails loudly (never falls back) when no
+sm_100 device is present.  No compute is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from rocwmma_fattn import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fa_fwd_sm100.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported():
+    names = _declared_functions()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(_capi.lib, n), f"{n} declared in include/fa_fwd_sm100.h but not exported"
+    assert sorted(_capi.EXPORTED_SYMBOLS) == names
+
+
+def test_abi_version_and_error_string():
+    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 1
+    assert isinstance(_capi.last_error(), str)
+
+
+def test_library_is_in_tree_and_native():
+    assert os.path.dirname(_capi.LIB_PATH).startswith(ROOT)
+    with open(_capi.LIB_PATH, "rb") as fh:
+        assert fh.read(4) == b"\x7fELF"
+
+
+def _st(B, H, N, D):
+    return (H * N * D, N * D, D, 1)
+
+
+@pytest.mark.parametrize(
+    "shape,expected",
+    [
+        ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # BASELINE sweep point
+        ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),      # BASELINE config 5
+        ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
+        ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad
+        ((3, 7, 1537, 1234, 111), _capi.FA_KERNEL_SIMT),      # unpadded odd head dim
+        ((1, 2, 300, 300, 256), _capi.FA_KERNEL_SIMT),        # head dim > 128
+        ((2, 4, 77, 300, 40), _capi.FA_KERNEL_TC1),
+    ],
+)
+def test_kernel_selection_is_pure_host_logic(shape, expected):
+    B, H, Nq, Nkv, D = shape
+    k = _capi.select_kernel(B, H, Nq, Nkv, D, _st(B, H, Nq, D), _st(B, H, Nkv, D), _st(B, H, Nkv, D),
+                            _st(B, H, Nq, D), _capi.FA_DTYPE_F16, False, D ** -0.5)
+    assert k == expected
+
+
+def test_kernel_selection_bnhd_strides_and_bad_strides():
+    B, H, N, D = 2, 8, 512, 128
+    bnhd = (N * H * D, D, H * D, 1)  # logical (b,h,n,d) strides of a [B,N,H,D] tensor
+    assert _capi.select_kernel(B, H, N, N, D, bnhd, bnhd, bnhd, bnhd, _capi.FA_DTYPE_BF16, True,
+                               0.1) == _capi.FA_KERNEL_WS
+    odd = (H * N * (D + 4), N * (D + 4), D + 4, 1)  # row stride not a multiple of 16 bytes
+    assert _capi.select_kernel(B, H, N, N, D, odd, odd, odd, odd, _capi.FA_DTYPE_F16, False,
+                               0.1) == _capi.FA_KERNEL_SIMT
+    with pytest.raises(_capi.FlashAttnError) as ei:
+        _capi.select_kernel(B, H, N, N, D, (1, 1, 1, 2), bnhd, bnhd, bnhd, _capi.FA_DTYPE_F16, False, 0.1)
+    assert ei.value.code == _capi.FA_ERR_INVALID_ARG and "stride" in str(ei.value)
+    # non-positive scale: handled by the generic kernel, not the tensor-core one
+    assert _capi.select_kernel(B, H, N, N, D, _st(B, H, N, D), _st(B, H, N, D), _st(B, H, N, D),
+                               _st(B, H, N, D), _capi.FA_DTYPE_F16, False, -1.0) == _capi.FA_KERNEL_SIMT
+
+
+@pytest.mark.parametrize(
+    "kw,code",
+    [
+        (dict(B=0), _capi.FA_ERR_INVALID_ARG),
+        (dict(Nkv=0), _capi.FA_ERR_INVALID_ARG),
+        (dict(dtype=7), _capi.FA_ERR_INVALID_ARG),
+        (dict(D=2048), _capi.FA_ERR_UNSUPPORTED),
+        (dict(scale=float("nan")), _capi.FA_ERR_INVALID_ARG),
+    ],
+)
+def test_argument_validation(kw, code):
+    a = dict(B=1, H=2, Nq=128, Nkv=128, D=64, dtype=_capi.FA_DTYPE_F16, scale=0.125)
+    a.update(kw)
+    st = _capi.strides4(_st(max(a["B"], 1), a["H"], a["Nq"], a["D"]))
+    rc = _capi.lib.fa_select_kernel(a["B"], a["H"], a["Nq"], a["Nkv"], a["D"], st, st, st, st,
+                                    a["dtype"], 0, a["scale"])
+    assert rc == -code
+    assert _capi.last_error() != ""
+
+
+def test_null_pointers_rejected_before_any_device_work():
+    st = _capi.strides4(_st(1, 2, 128, 64))
+    rc = _capi.lib.fa_fwd_sm100(None, None, None, None, None, 1, 2, 128, 128, 64, st, st, st, st, 0, 0,
+                                0.125, None)
+    assert rc == _capi.FA_ERR_INVALID_ARG
+    rc = _capi.lib.fa_fwd_sm100_host(None, None, None, None, None, 1, 2, 128, 128, 64, 0, 0, 0.125)
+    assert rc == _capi.FA_ERR_INVALID_ARG
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_device_fails_loudly_no_cpu_fallback():
+    buf = (ctypes.c_uint16 * (2 * 128 * 64))()
+    p = ctypes.addressof(buf)
+    st = _capi.strides4(_st(1, 2, 128, 64))
+    rc = _capi.lib.fa_fwd_sm100(p, p, p, p, None, 1, 2, 128, 128, 64, st, st, st, st, 0, 0, 0.125, None)
+    assert rc == _capi.FA_ERR_NO_DEVICE
+    assert "device" in _capi.last_error().lower()
+    assert _capi.launch_count() == 0
+
+
+def test_set_kernel_roundtrip():
+    prev = _capi.set_kernel(_capi.FA_KERNEL_SIMT)
+    try:
+        assert _capi.set_kernel(_capi.FA_KERNEL_AUTO) == _capi.FA_KERNEL_SIMT
+        with pytest.raises(ValueError):
+            _capi.set_kernel(99)
+    finally:
+        _capi.set_kernel(prev)

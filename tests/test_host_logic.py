@@ -1,0 +1,73 @@
+"""CPU tests of the Python host layer that mirrors /root/reference/rocwmma_fattn/FlashAttn.py:
+argument handling that needs no device, and the loud failure without one."""
+import inspect
+
+import pytest
+import torch
+
+from rocwmma_fattn import FlashAttn
+from rocwmma_fattn.FlashAttn import FlashAttentionFunction, _logical_shape, _logical_strides
+
+
+def test_signature_matches_reference_entry_point():
+    """FlashAttn.py:49 — forward(ctx, q, k, v, mask=None, causal=None, scale=None, BNHD_fmt=False, *args, **kwargs)"""
+    sig = inspect.signature(FlashAttentionFunction.forward)
+    names = list(sig.parameters)
+    assert names[:8] == ["ctx", "q", "k", "v", "mask", "causal", "scale", "BNHD_fmt"]
+    assert sig.parameters["mask"].default is None
+    assert sig.parameters["causal"].default is None
+    assert sig.parameters["scale"].default is None
+    assert sig.parameters["BNHD_fmt"].default is False
+    assert issubclass(FlashAttentionFunction, torch.autograd.Function)
+    assert hasattr(FlashAttn, "flash_attn_wmma") and hasattr(FlashAttn.flash_attn_wmma, "forward")
+
+
+def test_bnhd_stride_identity():
+    """The identity /root/reference/test_arrange.py:23-30 checks: element (b,h,n,d) of a [B,N,H,D]
+    tensor addressed through logical (b,h,n,d) strides equals the BHND-contiguous fetch."""
+    B, N, H, D = 2, 5, 3, 4
+    t = torch.arange(B * N * H * D).reshape(B, N, H, D)
+    st = _logical_strides(t, True)
+    assert _logical_shape(t, True) == (B, H, N, D)
+    bhnd = t.permute(0, 2, 1, 3).contiguous()
+    flat = t.reshape(-1)
+    for b, h, n, d in [(0, 0, 0, 0), (1, 2, 4, 3), (0, 1, 3, 2), (1, 0, 2, 1)]:
+        assert flat[b * st[0] + h * st[1] + n * st[2] + d * st[3]] == bhnd[b, h, n, d]
+    assert _logical_strides(bhnd, False) == bhnd.stride()
+
+
+def test_cpu_tensors_raise_no_fallback():
+    q = torch.rand(1, 2, 16, 8, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlashAttentionFunction.apply(q, q, q)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlashAttn.flash_attn_forward(q, q, q)
+
+
+def test_bad_rank_raises():
+    q = torch.rand(2, 16, 8)
+    with pytest.raises(ValueError):
+        FlashAttn.flash_attn_forward(q, q, q)
+
+
+def test_host_path_argument_checks():
+    q = torch.rand(1, 2, 16, 8, dtype=torch.float32)
+    with pytest.raises(TypeError):
+        FlashAttn.flash_attn_forward_host(q, q, q)
+    h = q.half()
+    with pytest.raises(ValueError):
+        FlashAttn.flash_attn_forward_host(h, h[:, :, :8], h[:, :1])
+    with pytest.raises(ValueError):
+        FlashAttn.flash_attn_forward_host(h.transpose(1, 2), h, h)  # not contiguous
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_host_path_fails_loudly_without_gpu():
+    h = torch.rand(1, 2, 16, 8).half()
+    with pytest.raises(RuntimeError, match="device"):
+        FlashAttn.flash_attn_forward_host(h, h, h)
+
+
+def test_backward_entry_is_explicit():
+    with pytest.raises(NotImplementedError):
+        FlashAttn.flash_attn_wmma.backward()
