@@ -31,6 +31,12 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
+#ifdef FA_TRACE
+unsigned long long* g_trace = nullptr;  // debug builds only (tools/trace_ws.py)
+#define FA_TP_TRACE , g_trace
+#else
+#define FA_TP_TRACE
+#endif
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -245,7 +251,7 @@ int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
-  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f};
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f FA_TP_TRACE};
   dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
   kernel<<<grid, 512, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
   FA_CUDA_TRY(cudaGetLastError());
@@ -261,7 +267,7 @@ int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
-  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f};
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f FA_TP_TRACE};
   dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
   kernel<<<grid, 128, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
   FA_CUDA_TRY(cudaGetLastError());
@@ -412,6 +418,10 @@ int ws_release(HostWs& w) {
 // exported C ABI
 // =================================================================================================
 extern "C" {
+
+#ifdef FA_TRACE
+void fa_trace_set(void* buf) { g_trace = static_cast<unsigned long long*>(buf); }
+#endif
 
 int fa_abi_version(void) { return FA_ABI_VERSION; }
 

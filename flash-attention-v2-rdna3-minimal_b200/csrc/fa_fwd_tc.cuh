@@ -19,6 +19,9 @@ struct TcParams {
   float* lse;            // [B,H,Nq] fp32, base-2 log-sum-exp of the scaled scores; may be null
   int Nq, Nkv, H;
   float scale_log2;      // scale * log2(e)
+#ifdef FA_TRACE
+  unsigned long long* trace;  // debug builds only: clock64() stamps of one CTA (tools/trace_ws.py)
+#endif
 };
 
 constexpr int kTileM = 128;  // query rows per tile

@@ -38,7 +38,24 @@ struct WsCfg {
   static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
 };
 
-constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the max grew by > 2^8
+// Debug-only timeline (-DFA_TRACE, never in the shipped library): lane 0 of each role's first warp
+// stamps clock64() into p.trace[role][j][event] for one CTA; see tools/trace_ws.py.
+#ifdef FA_TRACE
+#define FA_TR(role, j, ev)                                                                  \
+  do {                                                                                      \
+    if (tr_on && lane == 0) p.trace[((role) * 128 + ((j) & 127)) * 8 + (ev)] = clock64();   \
+  } while (0)
+#else
+#define FA_TR(role, j, ev) do { } while (0)
+#endif
+
+constexpr float kRescaleThreshold = 8.0f;
+
+// Of every 8 pairs of P elements, how many compute 2^x on the FMA pipes instead of the MUFU.
+#ifndef FA_EMU_PAIRS
+#define FA_EMU_PAIRS 2
+#endif
+constexpr int kEmuPairs = FA_EMU_PAIRS;  // log2 units: rescale O only when the max grew by > 2^8
 
 template <int kDP, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(512, 1)
@@ -79,6 +96,10 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int row0 = pair * 2 * kTileM;
+#ifdef FA_TRACE
+  const bool tr_on = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 &&
+                     blockIdx.z == 0;
+#endif
 
   // per-tile KV trip counts
   const int n_kv_total = (p.Nkv + kTileN - 1) / kTileN;
@@ -121,7 +142,12 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // The CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at lane 0,
+  // column 0.  Using the literal 0 keeps every TMEM address a compile-time constant; otherwise
+  // ptxas cannot prove the value read back from shared memory warp-uniform and wraps each
+  // tcgen05.mma in an ELECT / R2UR.BROADCAST loop that made the issuing thread the bottleneck.
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;
 
   if (warp >= 12) {
@@ -130,7 +156,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // =========================================================================================
     setmaxnreg_dec<64>();
     if (warp == 13) {
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (n_t[t] > 0) {
@@ -146,6 +172,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const int slot = idx % kS;
           const uint32_t use = idx / kS;
           mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
+          FA_TR(4, idx >> 1, idx & 1);
           mbar_arrive_expect_tx(bar_kv_full(slot), C::kTileBytes);
           const CUtensorMap* map = (idx & 1) ? &tmap_v : &tmap_k;
 #pragma unroll
@@ -156,7 +183,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       __syncwarp();
     } else if (warp == 12) {
-      if (lane == 0) {
+      if (elect_one()) {
         constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
         constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);
 
@@ -165,26 +192,26 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc_fence_after();
         };
         auto release_kv = [&](int idx) { tc_commit(bar_kv_empty(idx % kS)); };
+        constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
         auto issue_s = [&](int t, int j) {  // S_t = Q_t K_j^T
-          const uint32_t kbase = sKV + ((2 * j) % kS) * C::kTileBytes;
-          const uint32_t qbase = sQ + t * C::kTileBytes;
+          const uint32_t k_lo = smem_desc_lo(sKV + ((2 * j) % kS) * C::kTileBytes, 16);
+          const uint32_t q_lo = smem_desc_lo(sQ + t * C::kTileBytes, 16);
 #pragma unroll
           for (int k = 0; k < kKSteps; ++k) {
-            const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-            umma_ss(tmem + col_s(t), make_smem_desc_sw128(qbase + off, 16, 1024),
-                    make_smem_desc_sw128(kbase + off, 16, 1024), idesc_s, k > 0);
+            const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+            umma_ss2(tmem + col_s(t), q_lo + off, desc_hi, k_lo + off, desc_hi, idesc_s, k > 0);
           }
           tc_commit(bar_s_full(t));
         };
         auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
-          const uint32_t vbase = sKV + ((2 * j + 1) % kS) * C::kTileBytes;
+          const uint32_t v_lo = smem_desc_lo(sKV + ((2 * j + 1) % kS) * C::kTileBytes, 16384);
           mbar_wait(bar_po(t), j & 1, 31 + t);
           tc_fence_after();
+          FA_TR(2, j, 2 + 3 * t);
 #pragma unroll
           for (int k = 0; k < kTileN / 16; ++k) {
-            umma_ts(tmem + col_o(t), tmem + col_s(t) + k * 8,
-                    make_smem_desc_sw128(vbase + k * 2048, 16384, 1024), idesc_o,
-                    (j > 0) || (k > 0));
+            umma_ts2(tmem + col_o(t), tmem + col_s(t) + k * 8, v_lo + ((k * 2048) >> 4), desc_hi,
+                     idesc_o, (j > 0) || (k > 0));
           }
           if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
         };
@@ -204,14 +231,20 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll 1
         for (int j = 0; j < n_max; ++j) {
           const int nx = j + 1;
+          FA_TR(2, j, 0);
           wait_kv(2 * j + 1);
+          FA_TR(2, j, 1);
           if (j < n_t[0]) issue_pv(0, j);
+          FA_TR(2, j, 3);
           if (nx < n_max) wait_kv(2 * nx);
           if (nx < n_t[0]) issue_s(0, nx);
+          FA_TR(2, j, 4);
           if (j < n_t[1]) issue_pv(1, j);
+          FA_TR(2, j, 6);
           release_kv(2 * j + 1);
           if (nx < n_t[1]) issue_s(1, nx);
           if (nx < n_max) release_kv(2 * nx);
+          FA_TR(2, j, 7);
         }
       }
       __syncwarp();
@@ -234,13 +267,16 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
+      FA_TR(t, j, 0);
       mbar_wait(bar_s_full(t), j & 1, 40 + t);
       tc_fence_after();
+      FA_TR(t, j, 1);
       float s[kTileN];
 #pragma unroll
       for (int cidx = 0; cidx < 4; ++cidx)
         tmem_ld_x32(tS + cidx * 32, reinterpret_cast<uint32_t*>(s) + cidx * 32);
       tmem_wait_ld();
+      FA_TR(t, j, 2);
 
       const int col0 = j * kTileN;
       const bool tail = (col0 + kTileN > p.Nkv);
@@ -271,20 +307,32 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         sScale[t * 128 + r] = alpha;
         mbar_arrive(bar_scale(t));
       }
-      const float mc = m_run * c;
+      FA_TR(t, j, 3);
+      const float nmc = -m_run * c;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
       for (int i = 0; i < kTileN; i += 4) {
-        s[i] = ex2_approx(fmaf(s[i], c, -mc));
-        s[i + 1] = ex2_approx(fmaf(s[i + 1], c, -mc));
-        s[i + 2] = ex2_approx(fmaf(s[i + 2], c, -mc));
-        s[i + 3] = ex2_approx(fmaf(s[i + 3], c, -mc));
-        sum0 += s[i];
-        sum1 += s[i + 1];
-        sum2 += s[i + 2];
-        sum3 += s[i + 3];
+        // p = 2^(s*c - m*c): kEmuPairs of every 8 element pairs go through the FMA pipes
+        // (ex2_fma2), the rest through the MUFU
+        ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc, nmc);
+        ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc, nmc);
+        if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
+          ex2_fma2(s[i], s[i + 1]);
+        } else {
+          s[i] = ex2_approx(s[i]);
+          s[i + 1] = ex2_approx(s[i + 1]);
+        }
+        if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
+          ex2_fma2(s[i + 2], s[i + 3]);
+        } else {
+          s[i + 2] = ex2_approx(s[i + 2]);
+          s[i + 3] = ex2_approx(s[i + 3]);
+        }
+        fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
+        fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
       }
       l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      FA_TR(t, j, 4);
 
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
@@ -297,6 +345,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_po(t));
+      FA_TR(t, j, 5);
     }
 
     if (n > 0) {
@@ -321,6 +370,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (j < n_t[t]) {
           if (j > 0) {
             mbar_wait(bar_scale(t), (j - 1) & 1, 50 + t);
+            FA_TR(3, j, t);
             const float a = sScale[t * 128 + r];
             if (__any_sync(0xffffffffu, a != 1.f)) {
               tc_fence_after();

@@ -56,6 +56,79 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 operations per instruction)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1,
+                                      float c0, float c1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fsub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// 2^x for a pair of values on the FMA / ALU pipes instead of the MUFU (which sustains only 16
+// ex2 per clock per SM and is the co-bottleneck of the forward at head dim 128).  Cody-Waite:
+// n = round(x) through the 1.5 * 2^23 magic constant, f = x - n in [-0.5, 0.5], 2^f by a degree-3
+// minimax polynomial (relative error 7.5e-5, below the half-ulp of fp16), then n is added to the
+// exponent field.  Inputs are clamped to >= -120 (result ~1e-36, i.e. zero after the 16-bit
+// rounding of P); inputs must be <= 127.
+__device__ __forceinline__ void ex2_fma2(float& x0, float& x1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  constexpr float k0 = 0.9999280571937561f, k1 = 0.6932609677314758f, k2 = 0.2426111251115799f,
+                  k3 = 0.0551716685295105f;
+  x0 = fmaxf(x0, -120.f);
+  x1 = fmaxf(x1, -120.f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, kMagic, kMagic);
+  fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+  fsub2(f0, f1, x0, x1, n0, n1);
+  ffma2(p0, p1, f0, f1, k3, k3, k2, k2);
+  ffma2(p0, p1, p0, p1, f0, f1, k1, k1);
+  ffma2(p0, p1, p0, p1, f0, f1, k0, k0);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -213,6 +286,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
+// The same descriptor as two 32-bit halves.  The high word depends only on the layout (SBO,
+// version, swizzle), so it is a compile-time constant; the low word is the 14-bit address field
+// plus LBO << 16, and stepping the operand by `bytes` inside one tile is `lo + (bytes >> 4)` (no
+// carry out of the address field for smem addresses < 256 KB).  Keeping both halves in uniform
+// registers makes one tcgen05.mma cost a single UIADD3 + UTCHMMA on the issuing thread.
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
 // Instruction descriptor for kind::f16 (fp16 / bf16 operands, fp32 accumulate).
 //   [4,6) D format (1 = f32)   [7,10) A format   [10,13) B format  (0 = f16, 1 = bf16)
 //   [15] A major (0 = K)       [16] B major (0 = K, 1 = MN)
@@ -249,6 +334,36 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// split-descriptor forms (see smem_desc_lo / smem_desc_hi_sw128)
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                         uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 

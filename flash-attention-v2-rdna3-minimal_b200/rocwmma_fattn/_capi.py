@@ -11,7 +11,8 @@ import importlib.util
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
+# FA_FWD_SM100_LIB selects another build of the same C-ABI (e.g. the FA_TRACE debug library)
+LIB_PATH = os.environ.get("FA_FWD_SM100_LIB") or os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
 
 FA_ABI_VERSION = 1
 FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
