@@ -32,7 +32,7 @@ struct WsCfg {
   static constexpr int kQ = 0;                           // 2 Q tiles (re-used as O staging)
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 10 + 2 * kStages;
+  static constexpr int kNumBars = 14 + 2 * kStages;
   static constexpr int kScale = kBars + 8 * kNumBars + 16;  // float [2][128] rescale factors
   static constexpr int kFinal = kScale + 2 * 128 * 4;       // float [2][128] final row sums
   static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
@@ -49,13 +49,23 @@ struct WsCfg {
 #define FA_TR(role, j, ev) do { } while (0)
 #endif
 
-constexpr float kRescaleThreshold = 8.0f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when the max grew by > 2^8
 
 // Of every 8 pairs of P elements, how many compute 2^x on the FMA pipes instead of the MUFU.
 #ifndef FA_EMU_PAIRS
 #define FA_EMU_PAIRS 2
 #endif
-constexpr int kEmuPairs = FA_EMU_PAIRS;  // log2 units: rescale O only when the max grew by > 2^8
+constexpr int kEmuPairs = FA_EMU_PAIRS;
+// k-steps (16 keys each) of O += P V issued on the early hand-off; must be even (P is stored 32
+// columns at a time) and < 8.
+#ifndef FA_EARLY_K
+#define FA_EARLY_K 6
+#endif
+constexpr int kEarlyK = FA_EARLY_K;
+#ifndef FA_SEQ
+#define FA_SEQ 1
+#endif
+constexpr bool kSeq = FA_SEQ != 0;
 
 template <int kDP, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(512, 1)
@@ -84,10 +94,17 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_q_full = [&](int t) { return smem_u32(&bars[t]); };          // tx, count 1
   auto bar_s_full = [&](int t) { return smem_u32(&bars[2 + t]); };      // tcgen05.commit
   auto bar_scale = [&](int t) { return smem_u32(&bars[4 + t]); };       // 128 softmax threads
-  auto bar_po = [&](int t) { return smem_u32(&bars[6 + t]); };          // 128 softmax + 128 correction
+  // P is handed to the MMA warp in two parts so that O += P V starts while the last quarter of
+  // the row is still being exponentiated: "early" = first kEarlyK k-steps of P stored AND O rescaled
+  // (4 softmax warps + 4 correction warps, one arrival per warp), "late" = the rest of P.
+  auto bar_p_early = [&](int t) { return smem_u32(&bars[6 + t]); };
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[10 + s]); };    // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[10 + kS + s]); };  // tcgen05.commit
+  auto bar_p_late = [&](int t) { return smem_u32(&bars[10 + t]); };     // 4 softmax warps
+  // The two softmax warpgroups take turns in the max/exp section (4 warps arrive): running both
+  // sections at once halves the speed of each and lengthens both S -> P -> S chains.
+  auto bar_seq = [&](int t) { return smem_u32(&bars[12 + t]); };
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[14 + s]); };    // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[14 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -119,7 +136,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_q_full(t), 1);
       mbar_init(bar_s_full(t), 1);
       mbar_init(bar_scale(t), 128);
-      mbar_init(bar_po(t), 256);
+      mbar_init(bar_p_early(t), 8);
+      mbar_init(bar_p_late(t), 4);
+      mbar_init(bar_seq(t), 4);
       mbar_init(bar_o_final(t), 1);
     }
 #pragma unroll
@@ -205,13 +224,20 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         };
         auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
           const uint32_t v_lo = smem_desc_lo(sKV + ((2 * j + 1) % kS) * C::kTileBytes, 16384);
-          mbar_wait(bar_po(t), j & 1, 31 + t);
+          mbar_wait(bar_p_early(t), j & 1, 31 + t);
           tc_fence_after();
           FA_TR(2, j, 2 + 3 * t);
 #pragma unroll
-          for (int k = 0; k < kTileN / 16; ++k) {
+          for (int k = 0; k < kEarlyK; ++k) {
             umma_ts2(tmem + col_o(t), tmem + col_s(t) + k * 8, v_lo + ((k * 2048) >> 4), desc_hi,
                      idesc_o, (j > 0) || (k > 0));
+          }
+          mbar_wait(bar_p_late(t), j & 1, 35 + t);
+          tc_fence_after();
+#pragma unroll
+          for (int k = kEarlyK; k < kTileN / 16; ++k) {
+            umma_ts2(tmem + col_o(t), tmem + col_s(t) + k * 8, v_lo + ((k * 2048) >> 4), desc_hi,
+                     idesc_o, true);
           }
           if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
         };
@@ -276,6 +302,13 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int cidx = 0; cidx < 4; ++cidx)
         tmem_ld_x32(tS + cidx * 32, reinterpret_cast<uint32_t*>(s) + cidx * 32);
       tmem_wait_ld();
+      if (kSeq) {  // my turn?  tile 0 goes first; turn j of tile 1 follows turn j of tile 0
+        if (t == 0) {
+          if (j > 0 && j - 1 < n_t[1]) mbar_wait(bar_seq(0), (j - 1) & 1, 42);
+        } else {
+          if (j < n_t[0]) mbar_wait(bar_seq(1), j & 1, 43);
+        }
+      }
       FA_TR(t, j, 2);
 
       const int col0 = j * kTileN;
@@ -308,44 +341,58 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_arrive(bar_scale(t));
       }
       FA_TR(t, j, 3);
+      // p = 2^(s*c - m*c), 32 columns at a time: exponentiate, round to 16 bit, store over S.
+      // kEmuPairs of every 8 element pairs go through the FMA pipes (ex2_fma2), the rest through
+      // the MUFU.  The row sum is taken after the hand-off (the MMA does not need it).
       const float nmc = -m_run * c;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = q * 32; i < q * 32 + 32; i += 4) {
+          ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc, nmc);
+          ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc, nmc);
+          if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
+            ex2_fma2(s[i], s[i + 1]);
+          } else {
+            s[i] = ex2_approx(s[i]);
+            s[i + 1] = ex2_approx(s[i + 1]);
+          }
+          if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
+            ex2_fma2(s[i + 2], s[i + 3]);
+          } else {
+            s[i + 2] = ex2_approx(s[i + 2]);
+            s[i + 3] = ex2_approx(s[i + 3]);
+          }
+          pk[(i - q * 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
+          pk[((i - q * 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
+        }
+        tmem_st_x16(tS + q * 16, pk);
+        if (q * 2 + 2 == kEarlyK) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p_early(t));
+          FA_TR(t, j, 4);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_p_late(t));
+        if (kSeq) mbar_arrive(bar_seq(t ^ 1));
+      }
+      FA_TR(t, j, 5);
+
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
       for (int i = 0; i < kTileN; i += 4) {
-        // p = 2^(s*c - m*c): kEmuPairs of every 8 element pairs go through the FMA pipes
-        // (ex2_fma2), the rest through the MUFU
-        ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc, nmc);
-        ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc, nmc);
-        if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
-          ex2_fma2(s[i], s[i + 1]);
-        } else {
-          s[i] = ex2_approx(s[i]);
-          s[i + 1] = ex2_approx(s[i + 1]);
-        }
-        if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
-          ex2_fma2(s[i + 2], s[i + 3]);
-        } else {
-          s[i + 2] = ex2_approx(s[i + 2]);
-          s[i + 3] = ex2_approx(s[i + 3]);
-        }
         fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
         fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
       }
       l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      FA_TR(t, j, 4);
-
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          pk[i] = pack2<kBF16>(s[hlf * 64 + 2 * i], s[hlf * 64 + 2 * i + 1]);
-        tmem_st_x32(tS + hlf * 32, pk);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_po(t));
-      FA_TR(t, j, 5);
+      FA_TR(t, j, 6);
     }
 
     if (n > 0) {
@@ -387,7 +434,8 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
               tc_fence_before();
             }
           }
-          mbar_arrive(bar_po(t));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p_early(t));
         }
       }
     }

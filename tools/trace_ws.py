@@ -34,7 +34,7 @@ t = buf.cpu().view(5, 128, 8).numpy()
 nj = min(128, N // 128)
 base = t[2, 0, 0]
 out = {"N": N, "causal": causal, "roles": {}}
-names = {0: "softmax0 [wait_s, s_ready, ld_done, max_done, exp_done, p_arrived]",
+names = {0: "softmax0 [wait_s, s_ready, ld_done, max_done, p_early, p_late, sum_done]",
          1: "softmax1 [same]",
          2: "mma [iter_start, v_ready, po0_ready, pv0_issued, s0_issued, po1_ready, pv1_issued, iter_end]",
          3: "corr [scale0_seen, scale1_seen]", 4: "tma [k_slot_free, v_slot_free]"}
@@ -52,13 +52,13 @@ s0, s1, m = t[0], t[1], t[2]
 stats = {
     "period_mma": float(np.mean(np.diff(m[lo:hi, 0].astype(np.int64)))),
     "sm0_wait_s": d(s0[:, 1], s0[:, 0]), "sm0_ld": d(s0[:, 2], s0[:, 1]), "sm0_max": d(s0[:, 3], s0[:, 2]),
-    "sm0_exp": d(s0[:, 4], s0[:, 3]), "sm0_pst": d(s0[:, 5], s0[:, 4]),
+    "sm0_exp_early": d(s0[:, 4], s0[:, 3]), "sm0_exp_late": d(s0[:, 5], s0[:, 4]), "sm0_sum": d(s0[:, 6], s0[:, 5]),
     "sm1_wait_s": d(s1[:, 1], s1[:, 0]), "sm1_ld": d(s1[:, 2], s1[:, 1]), "sm1_max": d(s1[:, 3], s1[:, 2]),
-    "sm1_exp": d(s1[:, 4], s1[:, 3]), "sm1_pst": d(s1[:, 5], s1[:, 4]),
+    "sm1_exp_early": d(s1[:, 4], s1[:, 3]), "sm1_exp_late": d(s1[:, 5], s1[:, 4]), "sm1_sum": d(s1[:, 6], s1[:, 5]),
     "mma_wait_v": d(m[:, 1], m[:, 0]), "mma_wait_po0": d(m[:, 2], m[:, 1]), "mma_issue_pv0": d(m[:, 3], m[:, 2]),
     "mma_issue_s0": d(m[:, 4], m[:, 3]), "mma_wait_po1": d(m[:, 5], m[:, 4]), "mma_issue_pv1": d(m[:, 6], m[:, 5]),
     "mma_issue_s1": d(m[:, 7], m[:, 6]),
-    "p0_arrive_to_mma_seen": d(m[:, 2], s0[:, 5]), "p1_arrive_to_mma_seen": d(m[:, 5], s1[:, 5]),
+    "p0_early_to_mma_seen": d(m[:, 2], s0[:, 4]), "p1_early_to_mma_seen": d(m[:, 5], s1[:, 4]),
     # S_t(j+1) issued at m[j,4] / m[j,7]; softmax sees it at s[j+1,1]
     "s0_issue_to_ready": float(np.mean(s0[lo + 1:hi + 1, 1].astype(np.int64) - m[lo:hi, 4].astype(np.int64))),
     "s1_issue_to_ready": float(np.mean(s1[lo + 1:hi + 1, 1].astype(np.int64) - m[lo:hi, 7].astype(np.int64))),
