@@ -253,7 +253,7 @@ int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f FA_TP_TRACE};
   dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
-  kernel<<<grid, 512, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;

@@ -1,22 +1,32 @@
 // Warp-specialised tcgen05 forward kernel ("ws"): the fast path.
 //
 // One CTA = one (batch, head, 256-row Q block) = two 128-row Q tiles that ping-pong on the tensor
-// cores: while the softmax warpgroup of tile 0 works on S0(j) in registers, the tensor cores
-// compute S1(j) / O1 += P1 V, and vice versa.  16 warps:
+// cores: while the softmax warps of tile 0 work on S0(j) in registers, the tensor cores compute
+// S1(j) / O1 += P1 V, and vice versa.  20 warps:
 //
-//   warps  0- 3  softmax warpgroup for Q tile 0   (one thread = one query row = one TMEM lane)
-//   warps  4- 7  softmax warpgroup for Q tile 1
-//   warps  8-11  correction warpgroup: rescales the O accumulators in TMEM when a row max moved,
-//                and runs the epilogue (O / l -> 16 bit -> smem -> TMA store)
-//   warp  12     MMA issuer (one thread issues every tcgen05.mma)
-//   warp  13     TMA producer (Q once, then the K/V ring)
-//   warps 14-15  idle (they only donate their registers)
+//   warps  0- 7  softmax for Q tile 0: warp w owns TMEM lanes 32*(w%4).. (query rows) and the
+//                64-key half (w/4)%2 of every S tile, so one query row is shared by two threads
+//                on the same SM sub-partition; their partial row maxima meet through shared memory
+//   warps  8-15  softmax for Q tile 1
+//   warp  16     MMA issuer (one elected thread issues every tcgen05.mma)
+//   warp  17     TMA producer (Q once, then the K/V ring)
+//   warps 18-19  idle (they only donate their registers)
+//
+// Why two threads per row: the exp / max / pack stream of one 128-key row is ~650 dependent-issue
+// instructions; a single warp issues them at ~0.35 IPC, which made S -> P -> next S the critical
+// chain.  Two warps per row-quarter halve the chain and let the scheduler overlap MUFU, FMA and ALU
+// work of the two halves.  The softmax warps also rescale O (rarely: lazy rescale) and run the
+// epilogue, so there is no separate correction warpgroup polling barriers.
 //
 // TMEM (512 columns x 128 lanes x 32 bit):  S0 [0,128)  S1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
-// P (16-bit) overwrites the first 64 columns of its S tile and feeds the PV MMA from TMEM (TS form).
+// P (16-bit) of key half h overwrites S columns [64h, 64h+32) - inside the S columns the same
+// thread loaded - and feeds the PV MMA from TMEM (TS form).
 //
 // MMA issue order (K/V ring order is K0 V0 K1 V1 ...):
 //   S0(0) S1(0) | PV0(0) S0(1) PV1(0) S1(1) | PV0(1) S0(2) PV1(1) S1(2) | ...
+// PV is issued in two parts: the k-steps whose P columns were stored first ("early" barrier), then
+// the rest ("late"), so the tensor cores start on O += P V while the second half of the
+// exponentials is still in flight.
 //
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 / kernel_bf16.cu:329-576 and the
 // device GEMM helpers (:115-302); see fa_fwd_tc.cuh for the serial version of the same algorithm.
@@ -25,6 +35,8 @@
 
 namespace fa {
 
+constexpr int kWsThreads = 640;
+
 template <int kDP>
 struct WsCfg {
   static constexpr int kTileBytes = kTileM * kDP * 2;
@@ -32,10 +44,10 @@ struct WsCfg {
   static constexpr int kQ = 0;                           // 2 Q tiles (re-used as O staging)
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 14 + 2 * kStages;
-  static constexpr int kScale = kBars + 8 * kNumBars + 16;  // float [2][128] rescale factors
-  static constexpr int kFinal = kScale + 2 * 128 * 4;       // float [2][128] final row sums
-  static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
+  static constexpr int kNumBars = 12 + 2 * kStages;
+  static constexpr int kMax = kBars + 8 * kNumBars + 16;      // float [2 parity][2 tile][2 half][128]
+  static constexpr int kFinal = kMax + 2 * 2 * 2 * 128 * 4;   // float [2 tile][2 half][128] row sums
+  static constexpr int kTotal = kFinal + 2 * 2 * 128 * 4 + 1024;  // + alignment slack
 };
 
 // Debug-only timeline (-DFA_TRACE, never in the shipped library): lane 0 of each role's first warp
@@ -53,22 +65,17 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when th
 
 // Of every 8 pairs of P elements, how many compute 2^x on the FMA pipes instead of the MUFU.
 #ifndef FA_EMU_PAIRS
-#define FA_EMU_PAIRS 2
+#define FA_EMU_PAIRS 0
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
-// k-steps (16 keys each) of O += P V issued on the early hand-off; must be even (P is stored 32
-// columns at a time) and < 8.
-#ifndef FA_EARLY_K
-#define FA_EARLY_K 6
-#endif
-constexpr int kEarlyK = FA_EARLY_K;
+// The two softmax groups take turns in the max/exp section (experiment; off by default).
 #ifndef FA_SEQ
-#define FA_SEQ 1
+#define FA_SEQ 0
 #endif
 constexpr bool kSeq = FA_SEQ != 0;
 
 template <int kDP, bool kBF16, bool kCausal>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kWsThreads, 1)
 fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
                  const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v,
@@ -77,6 +84,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kS = C::kStages;
   constexpr int kDBlocks = kDP / 64;
   constexpr int kKSteps = kDP / 16;
+  constexpr int kOHalf = kDP / 2;  // O columns each of the two threads of a row owns
   auto col_s = [](int t) -> uint32_t { return static_cast<uint32_t>(t) * 128u; };
   auto col_o = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u; };
 
@@ -87,24 +95,20 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t sKV = smem_u32(smem + C::kKV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kBars + 8 * C::kNumBars);
-  float* sScale = reinterpret_cast<float*>(smem + C::kScale);
+  float* sMax = reinterpret_cast<float*>(smem + C::kMax);
   float* sFinal = reinterpret_cast<float*>(smem + C::kFinal);
 
   // barrier map
   auto bar_q_full = [&](int t) { return smem_u32(&bars[t]); };          // tx, count 1
   auto bar_s_full = [&](int t) { return smem_u32(&bars[2 + t]); };      // tcgen05.commit
-  auto bar_scale = [&](int t) { return smem_u32(&bars[4 + t]); };       // 128 softmax threads
-  // P is handed to the MMA warp in two parts so that O += P V starts while the last quarter of
-  // the row is still being exponentiated: "early" = first kEarlyK k-steps of P stored AND O rescaled
-  // (4 softmax warps + 4 correction warps, one arrival per warp), "late" = the rest of P.
-  auto bar_p_early = [&](int t) { return smem_u32(&bars[6 + t]); };
+  // P goes to the MMA warp in two parts (one arrival per softmax warp, 8 warps per tile):
+  // "early" = first 32 keys of each half stored AND O rescaled, "late" = the other 32 of each half.
+  auto bar_p_early = [&](int t) { return smem_u32(&bars[4 + t]); };
+  auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
-  auto bar_p_late = [&](int t) { return smem_u32(&bars[10 + t]); };     // 4 softmax warps
-  // The two softmax warpgroups take turns in the max/exp section (4 warps arrive): running both
-  // sections at once halves the speed of each and lengthens both S -> P -> S chains.
-  auto bar_seq = [&](int t) { return smem_u32(&bars[12 + t]); };
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[14 + s]); };    // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[14 + kS + s]); };  // tcgen05.commit
+  auto bar_seq = [&](int t) { return smem_u32(&bars[10 + t]); };        // kSeq only, 8 warps
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[12 + s]); };    // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[12 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -114,8 +118,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int b = blockIdx.z;
   const int row0 = pair * 2 * kTileM;
 #ifdef FA_TRACE
-  const bool tr_on = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 &&
-                     blockIdx.z == 0;
+  const bool tr_cta = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 &&
+                      blockIdx.z == 0;
+  const bool tr_on = tr_cta && (warp >= 16 || (warp & 7) == 0 || warp == 4);  // warp 4: partner of warp 0
 #endif
 
   // per-tile KV trip counts
@@ -130,16 +135,15 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   }
   const int n_max = max(n_t[0], n_t[1]);
 
-  if (warp == 12 && lane == 0) {
+  if (warp == 16 && lane == 0) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_q_full(t), 1);
       mbar_init(bar_s_full(t), 1);
-      mbar_init(bar_scale(t), 128);
       mbar_init(bar_p_early(t), 8);
-      mbar_init(bar_p_late(t), 4);
-      mbar_init(bar_seq(t), 4);
+      mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
+      mbar_init(bar_seq(t), 8);
     }
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
@@ -148,13 +152,13 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     fence_mbar_init();
   }
-  if (warp == 13 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
   }
-  if (warp == 12) {
+  if (warp == 16) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -168,13 +172,19 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;
+#ifdef FA_TRACE
+  if (tr_cta && tid == 0) {  // SM clock during the kernel = d(clock64) / d(globaltimer)
+    p.trace[(4 * 128) * 8 + 4] = clock64();
+    p.trace[(4 * 128) * 8 + 5] = globaltimer_ns();
+  }
+#endif
 
-  if (warp >= 12) {
+  if (warp >= 16) {
     // =========================================================================================
-    // warpgroup 3: MMA issuer (warp 12), TMA producer (warp 13)
+    // warpgroup 4: MMA issuer (warp 16), TMA producer (warp 17)
     // =========================================================================================
-    setmaxnreg_dec<64>();
-    if (warp == 13) {
+    setmaxnreg_dec<32>();
+    if (warp == 17) {
       if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -201,7 +211,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
       __syncwarp();
-    } else if (warp == 12) {
+    } else if (warp == 16) {
       if (elect_one()) {
         constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
         constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);
@@ -222,23 +232,27 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           tc_commit(bar_s_full(t));
         };
+        // k-step ks covers keys [16 ks, 16 ks + 16): P columns of half ks/4 at S column
+        // 64 (ks/4) + 8 (ks%4); V rows 16 ks of the tile (2048 bytes apart in the MN-major tile)
+        auto pv_step = [&](int t, uint32_t v_lo, int ks, uint32_t acc) {
+          umma_ts2(tmem + col_o(t), tmem + col_s(t) + (ks >> 2) * 64 + (ks & 3) * 8,
+                   v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
+        };
         auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
           const uint32_t v_lo = smem_desc_lo(sKV + ((2 * j + 1) % kS) * C::kTileBytes, 16384);
           mbar_wait(bar_p_early(t), j & 1, 31 + t);
           tc_fence_after();
           FA_TR(2, j, 2 + 3 * t);
-#pragma unroll
-          for (int k = 0; k < kEarlyK; ++k) {
-            umma_ts2(tmem + col_o(t), tmem + col_s(t) + k * 8, v_lo + ((k * 2048) >> 4), desc_hi,
-                     idesc_o, (j > 0) || (k > 0));
-          }
+          pv_step(t, v_lo, 0, j > 0);
+          pv_step(t, v_lo, 1, 1);
+          pv_step(t, v_lo, 4, 1);
+          pv_step(t, v_lo, 5, 1);
           mbar_wait(bar_p_late(t), j & 1, 35 + t);
           tc_fence_after();
-#pragma unroll
-          for (int k = kEarlyK; k < kTileN / 16; ++k) {
-            umma_ts2(tmem + col_o(t), tmem + col_s(t) + k * 8, v_lo + ((k * 2048) >> 4), desc_hi,
-                     idesc_o, true);
-          }
+          pv_step(t, v_lo, 2, 1);
+          pv_step(t, v_lo, 3, 1);
+          pv_step(t, v_lo, 6, 1);
+          pv_step(t, v_lo, 7, 1);
           if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
         };
 
@@ -275,32 +289,39 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       __syncwarp();
     }
-  } else if (warp < 8) {
+  } else {
     // =========================================================================================
-    // softmax warpgroups
+    // softmax warps (0-7: tile 0, 8-15: tile 1)
     // =========================================================================================
-    setmaxnreg_inc<184>();
-    const int t = warp >> 2;
-    const int r = tid & 127;
+    setmaxnreg_inc<112>();  // 512 x 112 + 128 x 32 = 640 x 96: setmaxnreg only redistributes the CTA's launch allocation
+    const int t = warp >> 3;
+    const int half = (warp >> 2) & 1;
+#ifdef FA_TRACE
+    const int tr_role = (warp == 4) ? 3 : t;
+#endif
+    const int r = (warp & 3) * 32 + lane;  // query row inside the tile = TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem + lane_base + col_s(t);
+    const uint32_t tS = tmem + lane_base + col_s(t) + half * 64;  // my 64 S columns; P over [0,32)
+    const uint32_t tO = tmem + lane_base + col_o(t) + half * kOHalf;
+    const int pair_bar = 1 + t * 4 + (warp & 3);  // named barrier of the two warps sharing my rows
     const int tile_row0 = row0 + t * kTileM;
     const int diag_j = tile_row0 / kTileN;
     const int n = n_t[t];
+    float* my_max = sMax + (t * 2 + half) * 128 + r;
+    const float* other_max = sMax + (t * 2 + (half ^ 1)) * 128 + r;
 
     float m_run = -INFINITY;
-    float l_run = 0.f;
+    float l_run = 0.f;  // partial row sum over my key half
 
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
-      FA_TR(t, j, 0);
+      FA_TR(tr_role, j, 0);
       mbar_wait(bar_s_full(t), j & 1, 40 + t);
       tc_fence_after();
-      FA_TR(t, j, 1);
-      float s[kTileN];
-#pragma unroll
-      for (int cidx = 0; cidx < 4; ++cidx)
-        tmem_ld_x32(tS + cidx * 32, reinterpret_cast<uint32_t*>(s) + cidx * 32);
+      FA_TR(tr_role, j, 1);
+      float s[64];
+      tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
+      tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
       if (kSeq) {  // my turn?  tile 0 goes first; turn j of tile 1 follows turn j of tile 0
         if (t == 0) {
@@ -309,44 +330,57 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (j < n_t[0]) mbar_wait(bar_seq(1), j & 1, 43);
         }
       }
-      FA_TR(t, j, 2);
+      FA_TR(tr_role, j, 2);
 
-      const int col0 = j * kTileN;
-      const bool tail = (col0 + kTileN > p.Nkv);
+      const int col0 = j * kTileN + half * 64;  // first key of my half
+      const bool tail = (col0 + 64 > p.Nkv);
       const bool diag = kCausal && (j == diag_j);
       if (tail || diag) {
-        const int valid = tail ? (p.Nkv - col0) : kTileN;
-        const int lim = diag ? min(valid, r + 1) : valid;  // columns [0, lim) are visible
+        const int valid = tail ? (p.Nkv - col0) : 64;
+        const int lim = diag ? min(valid, r + 1 - half * 64) : valid;  // columns [0, lim) visible
 #pragma unroll
-        for (int i = 0; i < kTileN; ++i)
+        for (int i = 0; i < 64; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
 
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int i = 4; i < kTileN; i += 4) {
+      for (int i = 4; i < 64; i += 4) {
         mx0 = fmaxf(mx0, s[i]);
         mx1 = fmaxf(mx1, s[i + 1]);
         mx2 = fmaxf(mx2, s[i + 2]);
         mx3 = fmaxf(mx3, s[i + 3]);
       }
-      const float m_cand = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_run);
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      my_max[(j & 1) * 512] = mx;
+      named_bar_sync(pair_bar, 64);
+      const float m_cand = fmaxf(fmaxf(mx, other_max[(j & 1) * 512]), m_run);
+      // both threads of the row see the same three numbers, so they take the same decision
       float alpha = 1.f;
       if ((m_cand - m_run) * c > kRescaleThreshold) {  // also true for the first tile (m_run = -inf)
         alpha = ex2_approx((m_run - m_cand) * c);
         m_run = m_cand;
       }
-      if (j > 0) {
-        sScale[t * 128 + r] = alpha;
-        mbar_arrive(bar_scale(t));
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        // rare (lazy rescale): O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was
+        // issued before S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
+#pragma unroll 1
+        for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
+          uint32_t o[8];
+          tmem_ld_x8(tO + c8, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x8(tO + c8, o);
+        }
       }
-      FA_TR(t, j, 3);
+      FA_TR(tr_role, j, 3);
       // p = 2^(s*c - m*c), 32 columns at a time: exponentiate, round to 16 bit, store over S.
       // kEmuPairs of every 8 element pairs go through the FMA pipes (ex2_fma2), the rest through
       // the MUFU.  The row sum is taken after the hand-off (the MMA does not need it).
       const float nmc = -m_run * c;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = q * 32; i < q * 32 + 32; i += 4) {
@@ -368,121 +402,79 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           pk[((i - q * 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
         }
         tmem_st_x16(tS + q * 16, pk);
-        if (q * 2 + 2 == kEarlyK) {
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_p_early(t));
-          FA_TR(t, j, 4);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (q == 0) {
+            mbar_arrive(bar_p_early(t));
+          } else {
+            mbar_arrive(bar_p_late(t));
+            if (kSeq) mbar_arrive(bar_seq(t ^ 1));
+          }
         }
+        FA_TR(tr_role, j, 4 + q);
       }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_p_late(t));
-        if (kSeq) mbar_arrive(bar_seq(t ^ 1));
-      }
-      FA_TR(t, j, 5);
 
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < kTileN; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
         fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
       }
       l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
-      FA_TR(t, j, 6);
+      FA_TR(tr_role, j, 6);
     }
 
+    // ---- epilogue: O / l -> 16 bit -> swizzled smem (the tile's Q buffer) -> TMA store
     if (n > 0) {
-      sFinal[t * 128 + r] = l_run;
-      mbar_arrive(bar_scale(t));
+      sFinal[(t * 2 + half) * 128 + r] = l_run;
+      named_bar_sync(pair_bar, 64);
+      const float l_tot = l_run + sFinal[(t * 2 + (half ^ 1)) * 128 + r];
       const int row = tile_row0 + r;
-      if (p.lse != nullptr && row < p.Nq)
-        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + row] = m_run * c + log2f(l_run);
-    }
-  } else {
-    // =========================================================================================
-    // correction warpgroup (warps 8-11)
-    // =========================================================================================
-    setmaxnreg_dec<80>();
-    const int r = tid & 127;
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-
-#pragma unroll 1
-    for (int j = 0; j < n_max; ++j) {
+      if (half == 0 && p.lse != nullptr && row < p.Nq)
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + row] = m_run * c + log2f(l_tot);
+      const float inv_l = 1.f / l_tot;
+      mbar_wait(bar_o_final(t), 0, 54 + t);  // every MMA of this tile is done: Q_t is free too
+      tc_fence_after();
+      uint8_t* stage = smem + C::kQ + t * C::kTileBytes;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (j < n_t[t]) {
-          if (j > 0) {
-            mbar_wait(bar_scale(t), (j - 1) & 1, 50 + t);
-            FA_TR(3, j, t);
-            const float a = sScale[t * 128 + r];
-            if (__any_sync(0xffffffffu, a != 1.f)) {
-              tc_fence_after();
+      for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
+        uint32_t o[32];
+        tmem_ld_x32(tO + cidx * 32, o);
+        tmem_wait_ld();
 #pragma unroll
-              for (int cidx = 0; cidx < kDP / 32; ++cidx) {
-                uint32_t o[32];
-                tmem_ld_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * a);
-                tmem_st_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
-              }
-              tmem_wait_st();
-              tc_fence_before();
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_p_early(t));
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 val;
+          val.x = pack2<kBF16>(__uint_as_float(o[ch * 8 + 0]) * inv_l, __uint_as_float(o[ch * 8 + 1]) * inv_l);
+          val.y = pack2<kBF16>(__uint_as_float(o[ch * 8 + 2]) * inv_l, __uint_as_float(o[ch * 8 + 3]) * inv_l);
+          val.z = pack2<kBF16>(__uint_as_float(o[ch * 8 + 4]) * inv_l, __uint_as_float(o[ch * 8 + 5]) * inv_l);
+          val.w = pack2<kBF16>(__uint_as_float(o[ch * 8 + 6]) * inv_l, __uint_as_float(o[ch * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kOHalf + cidx * 32 + ch * 8)) = val;
         }
       }
-    }
-
-    // epilogue
+      fence_proxy_async_smem();
+      named_bar_sync(9 + t, 256);
+      if ((warp & 7) == 0 && lane == 0) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (n_t[t] > 0) {
-        mbar_wait(bar_scale(t), (n_t[t] - 1) & 1, 52 + t);
-        const float inv_l = 1.f / sFinal[t * 128 + r];
-        mbar_wait(bar_o_final(t), 0, 54 + t);
-        tc_fence_after();
-        uint8_t* stage = smem + C::kQ + t * C::kTileBytes;
-#pragma unroll
-        for (int cidx = 0; cidx < kDP / 32; ++cidx) {
-          uint32_t o[32];
-          tmem_ld_x32(tmem + lane_base + col_o(t) + cidx * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 val;
-            val.x = pack2<kBF16>(__uint_as_float(o[ch * 8 + 0]) * inv_l, __uint_as_float(o[ch * 8 + 1]) * inv_l);
-            val.y = pack2<kBF16>(__uint_as_float(o[ch * 8 + 2]) * inv_l, __uint_as_float(o[ch * 8 + 3]) * inv_l);
-            val.z = pack2<kBF16>(__uint_as_float(o[ch * 8 + 4]) * inv_l, __uint_as_float(o[ch * 8 + 5]) * inv_l);
-            val.w = pack2<kBF16>(__uint_as_float(o[ch * 8 + 6]) * inv_l, __uint_as_float(o[ch * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, cidx * 32 + ch * 8)) = val;
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (r == 0) {
-#pragma unroll
-          for (int db = 0; db < kDBlocks; ++db)
-            tma_store_4d(&tmap_o, sQ + t * C::kTileBytes + db * 16384, db * 64, row0 + t * kTileM,
-                         h, b);
-          tma_store_commit();
-        }
-        __syncwarp();
+        for (int db = 0; db < kDBlocks; ++db)
+          tma_store_4d(&tmap_o, sQ + t * C::kTileBytes + db * 16384, db * 64, row0 + t * kTileM, h, b);
+        tma_store_commit();
+        tma_store_wait_read();
       }
+      __syncwarp();
     }
-    if (r == 0) tma_store_wait_read();
-    __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem, 512);
+#ifdef FA_TRACE
+  if (tr_cta && tid == 0) {
+    p.trace[(4 * 128) * 8 + 6] = clock64();
+    p.trace[(4 * 128) * 8 + 7] = globaltimer_ns();
+  }
+#endif
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace fa

@@ -1,8 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest.log
-tail -3 gpurun_out/pytest.log
 timeout 900 python tools/ab_bench.py $AB_VARIANTS
-timeout 300 python tools/trace_ws.py 16384 > gpurun_out/trace16k.log 2>&1
-tail -26 gpurun_out/trace16k.log

@@ -1,0 +1,143 @@
+// Pipe-rate microbenchmark for the softmax instruction mix of the forward kernel (sm_100a).
+// One CTA per SM, W warps per CTA (W/4 per SM sub-partition); every warp runs an unrolled stream of
+// independent operations of one kind (or a mix) and lane 0 reports clock64() per warp-instruction.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/microbench tools/microbench_pipes.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+
+#define REP 64
+#define ITERS 200
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void ffma2(float& a, float& b, float c, float d) {
+  asm volatile("{.reg .b64 ra, rb, rc; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%2}; mov.b64 rc, {%3,%3};"
+               "fma.rn.f32x2 ra, ra, rb, rc; mov.b64 {%0,%1}, ra;}" : "+f"(a), "+f"(b) : "f"(c), "f"(d));
+}
+__device__ __forceinline__ void fadd2(float& a, float& b, float c) {
+  asm volatile("{.reg .b64 ra, rb; mov.b64 ra, {%0,%1}; mov.b64 rb, {%2,%2};"
+               "add.rn.f32x2 ra, ra, rb; mov.b64 {%0,%1}, ra;}" : "+f"(a), "+f"(b) : "f"(c));
+}
+__device__ __forceinline__ void ffma1(float& a, float c, float d) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(c), "f"(d)); }
+__device__ __forceinline__ void fmax3(float& a, float b, float c) { asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(b), "f"(c)); }
+__device__ __forceinline__ void fmax2(float& a, float b) { asm volatile("max.f32 %0, %0, %1;" : "+f"(a) : "f"(b)); }
+__device__ __forceinline__ void f2fp(uint32_t& d, float a, float b) { asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); }
+__device__ __forceinline__ void imadshl(int& a, int b) { asm volatile("mad.lo.s32 %0, %1, 8388608, %0;" : "+r"(a) : "r"(b)); }
+
+// kind: 0 MUFU  1 FFMA2  2 FFMA  3 FADD2  4 FMNMX3  5 FMNMX  6 F2FP  7 IMAD
+//       8 MUFU+FFMA2 (1:1)  9 MUFU+FMNMX3 (1:1)  10 FFMA2+FMNMX3  11 FFMA2+F2FP  12 MUFU+FFMA2+F2FP (2:1:1)
+//       13 softmax-like per 4 elems: 2 FFMA2, 4 MUFU, 2 F2FP, 2 FADD2, 1.3 FMNMX3
+template <int KIND>
+__global__ void bench(long long* out, float seed) {
+  float x[8];
+  uint32_t u[4] = {0, 0, 0, 0};
+  int n[4] = {1, 2, 3, 4};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = seed + i * 0.001f + threadIdx.x * 1e-6f;
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int r = 0; r < REP / 8; ++r) {
+      if (KIND == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ex2(x[i]);
+      } else if (KIND == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ffma2(x[i], x[(i + 1) & 7], 0.999f, 0.001f);
+      } else if (KIND == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ffma1(x[i], 0.999f, 0.001f);
+      } else if (KIND == 3) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fadd2(x[i], x[(i + 1) & 7], 0.001f);
+      } else if (KIND == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fmax3(x[i], x[(i + 3) & 7], x[(i + 5) & 7]);
+      } else if (KIND == 5) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fmax2(x[i], x[(i + 3) & 7]);
+      } else if (KIND == 6) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f2fp(u[i & 3], x[i], x[(i + 1) & 7]);
+      } else if (KIND == 7) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) imadshl(n[i & 3], n[(i + 1) & 3]);
+      } else if (KIND == 8) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { x[i] = ex2(x[i]); ffma2(x[4 + (i & 1) * 2], x[5 + (i & 1) * 2], 0.999f, 0.001f); }
+      } else if (KIND == 9) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { x[i] = ex2(x[i]); fmax3(x[4 + i], x[(i + 1) & 3], x[(i + 2) & 3]); }
+      } else if (KIND == 10) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ffma2(x[(i & 1) * 2], x[(i & 1) * 2 + 1], 0.999f, 0.001f); fmax3(x[4 + i], x[4 + ((i + 1) & 3)], x[4 + ((i + 2) & 3)]); }
+      } else if (KIND == 11) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ffma2(x[(i & 1) * 2], x[(i & 1) * 2 + 1], 0.999f, 0.001f); f2fp(u[i], x[4 + i], x[4 + ((i + 1) & 3)]); }
+      } else if (KIND == 12) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { x[i * 2] = ex2(x[i * 2]); ffma2(x[4 + i * 2], x[5 + i * 2], 0.999f, 0.001f); x[i * 2 + 1] = ex2(x[i * 2 + 1]); f2fp(u[i], x[i * 2], x[i * 2 + 1]); }
+      } else if (KIND == 13) {
+        // 8 "instructions slots" = 4 elements' worth twice is awkward; do one group of 4 elements:
+        // 2 FFMA2 + 4 MUFU + 2 F2FP + 2 FADD2 + 1 FMNMX3 = 11 instrs (counted as 8 for the report /8*11)
+        ffma2(x[0], x[1], 0.999f, 0.001f);
+        ffma2(x[2], x[3], 0.999f, 0.001f);
+        x[0] = ex2(x[0]); x[1] = ex2(x[1]); x[2] = ex2(x[2]); x[3] = ex2(x[3]);
+        f2fp(u[0], x[0], x[1]); f2fp(u[1], x[2], x[3]);
+        fadd2(x[4], x[5], x[0]); fadd2(x[6], x[7], x[2]);
+        fmax3(x[4], x[1], x[3]);
+      }
+    }
+  }
+  long long t1 = clock64();
+  float acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += x[i];
+  acc += u[0] + u[1] + u[2] + u[3] + n[0] + n[1] + n[2] + n[3];
+  if (acc == 12345.678f) out[1023] = 1;
+  if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = t1 - t0;
+}
+
+template <int KIND>
+void run(const char* name, long long* d_out, int instr_per_rep8) {
+  const int warps[] = {4, 8, 16};
+  printf("%-28s", name);
+  for (int w : warps) {
+    bench<KIND><<<148, w * 32>>>(d_out, 0.5f);
+    cudaDeviceSynchronize();
+    bench<KIND><<<148, w * 32>>>(d_out, 0.5f);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 32);
+    cudaMemcpy(h.data(), d_out, h.size() * 8, cudaMemcpyDeviceToHost);
+    double mx = 0;
+    for (int b = 0; b < 148; ++b)
+      for (int i = 0; i < w; ++i) mx = mx > h[b * 32 + i] ? mx : (double)h[b * 32 + i];
+    const double n_instr = (double)ITERS * (REP / 8) * instr_per_rep8;  // per warp
+    // cycles per warp-instruction per SMSP = elapsed / (instr per warp * warps per SMSP)
+    printf("  w/smsp=%d: %6.2f cyc/instr/warp  %5.2f cyc/instr/smsp", w / 4, mx / n_instr, mx / (n_instr * (w / 4)));
+  }
+  printf("\n");
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 1024 * 8 * 8);
+  run<0>("MUFU.EX2", d_out, 8);
+  run<1>("FFMA2", d_out, 8);
+  run<2>("FFMA", d_out, 8);
+  run<3>("FADD2", d_out, 8);
+  run<4>("FMNMX3", d_out, 8);
+  run<5>("FMNMX", d_out, 8);
+  run<6>("F2FP.F16x2", d_out, 8);
+  run<7>("IMAD(shl23+add)", d_out, 8);
+  run<8>("MUFU+FFMA2 1:1", d_out, 8);
+  run<9>("MUFU+FMNMX3 1:1", d_out, 8);
+  run<10>("FFMA2+FMNMX3 1:1", d_out, 8);
+  run<11>("FFMA2+F2FP 1:1", d_out, 8);
+  run<12>("MUFU+FFMA2+F2FP 2:1:1", d_out, 8);
+  run<13>("softmax mix (11 instr)", d_out, 11);
+  cudaError_t e = cudaGetLastError();
+  printf("status: %s\n", cudaGetErrorString(e));
+  return 0;
+}

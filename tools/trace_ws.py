@@ -18,10 +18,11 @@ from rocwmma_fattn.FlashAttn import FlashAttentionFunction
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 causal = len(sys.argv) > 2 and sys.argv[2] == "causal"
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2  # launches before the traced one (clock state)
 torch.manual_seed(0)
 q, k, v = (torch.rand(1, 16, N, 128, dtype=torch.float16, device="cuda") for _ in range(3))
 buf = torch.zeros(5 * 128 * 8, dtype=torch.int64, device="cuda")
-for _ in range(2):
+for _ in range(warm):
     FlashAttentionFunction.apply(q, k, v, None, causal)
 torch.cuda.synchronize()
 _capi.lib.fa_trace_set.argtypes = [ctypes.c_void_p]
@@ -37,7 +38,7 @@ out = {"N": N, "causal": causal, "roles": {}}
 names = {0: "softmax0 [wait_s, s_ready, ld_done, max_done, p_early, p_late, sum_done]",
          1: "softmax1 [same]",
          2: "mma [iter_start, v_ready, po0_ready, pv0_issued, s0_issued, po1_ready, pv1_issued, iter_end]",
-         3: "corr [scale0_seen, scale1_seen]", 4: "tma [k_slot_free, v_slot_free]"}
+         3: "softmax0 partner warp 4 [same as softmax0]", 4: "tma [k_slot_free, v_slot_free]"}
 for role in range(5):
     print("#", names[role])
     for j in list(range(0, min(nj, 6))) + list(range(max(6, nj // 2), min(nj, nj // 2 + 6))):
@@ -48,13 +49,17 @@ import numpy as np
 lo, hi = nj // 4, 3 * nj // 4
 def d(a, b):
     return float(np.mean(a[lo:hi].astype(np.int64) - b[lo:hi].astype(np.int64)))
-s0, s1, m = t[0], t[1], t[2]
+s0, s1, m, s0b = t[0], t[1], t[2], t[3]
 stats = {
     "period_mma": float(np.mean(np.diff(m[lo:hi, 0].astype(np.int64)))),
     "sm0_wait_s": d(s0[:, 1], s0[:, 0]), "sm0_ld": d(s0[:, 2], s0[:, 1]), "sm0_max": d(s0[:, 3], s0[:, 2]),
     "sm0_exp_early": d(s0[:, 4], s0[:, 3]), "sm0_exp_late": d(s0[:, 5], s0[:, 4]), "sm0_sum": d(s0[:, 6], s0[:, 5]),
     "sm1_wait_s": d(s1[:, 1], s1[:, 0]), "sm1_ld": d(s1[:, 2], s1[:, 1]), "sm1_max": d(s1[:, 3], s1[:, 2]),
     "sm1_exp_early": d(s1[:, 4], s1[:, 3]), "sm1_exp_late": d(s1[:, 5], s1[:, 4]), "sm1_sum": d(s1[:, 6], s1[:, 5]),
+    "sm0b_wait_s": d(s0b[:, 1], s0b[:, 0]), "sm0b_ld": d(s0b[:, 2], s0b[:, 1]), "sm0b_max": d(s0b[:, 3], s0b[:, 2]),
+    "sm0b_exp_early": d(s0b[:, 4], s0b[:, 3]), "sm0b_exp_late": d(s0b[:, 5], s0b[:, 4]), "sm0b_sum": d(s0b[:, 6], s0b[:, 5]),
+    "sm0_vs_sm0b_s_ready": d(s0b[:, 1], s0[:, 1]), "sm0_vs_sm0b_max_done": d(s0b[:, 3], s0[:, 3]),
+    "mma_commit_s0_to_sm0_ready": float(np.mean(s0[lo + 1:hi + 1, 1].astype(np.int64) - m[lo:hi, 4].astype(np.int64))),
     "mma_wait_v": d(m[:, 1], m[:, 0]), "mma_wait_po0": d(m[:, 2], m[:, 1]), "mma_issue_pv0": d(m[:, 3], m[:, 2]),
     "mma_issue_s0": d(m[:, 4], m[:, 3]), "mma_wait_po1": d(m[:, 5], m[:, 4]), "mma_issue_pv1": d(m[:, 6], m[:, 5]),
     "mma_issue_s1": d(m[:, 7], m[:, 6]),
@@ -63,6 +68,10 @@ stats = {
     "s0_issue_to_ready": float(np.mean(s0[lo + 1:hi + 1, 1].astype(np.int64) - m[lo:hi, 4].astype(np.int64))),
     "s1_issue_to_ready": float(np.mean(s1[lo + 1:hi + 1, 1].astype(np.int64) - m[lo:hi, 7].astype(np.int64))),
 }
+c0, g0, c1, g1 = (int(x) for x in t[4, 0, 4:8])
+stats["cta_cycles"] = c1 - c0
+stats["cta_ns"] = g1 - g0
+stats["sm_mhz_in_kernel"] = round((c1 - c0) / max(1, g1 - g0) * 1e3, 1)
 print(json.dumps(stats, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"trace_ws_n{N}{'_causal' if causal else ''}.json"), "w") as fh:
