@@ -65,7 +65,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when th
 
 // Of every 8 pairs of P elements, how many compute 2^x on the FMA pipes instead of the MUFU.
 #ifndef FA_EMU_PAIRS
-#define FA_EMU_PAIRS 0
+#define FA_EMU_PAIRS 1
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
 // The two softmax groups take turns in the max/exp section (experiment; off by default).
@@ -335,90 +335,125 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int col0 = j * kTileN + half * 64;  // first key of my half
       const bool tail = (col0 + 64 > p.Nkv);
       const bool diag = kCausal && (j == diag_j);
-      if (tail || diag) {
+      const bool masked = tail || diag;
+      int lim = 64;  // columns [0, lim) of my half are visible
+      if (masked) {
         const int valid = tail ? (p.Nkv - col0) : 64;
-        const int lim = diag ? min(valid, r + 1 - half * 64) : valid;  // columns [0, lim) visible
+        lim = diag ? min(valid, r + 1 - half * 64) : valid;
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= lim) s[i] = -INFINITY;
       }
 
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      // p = 2^(s*c - m*c) for one group of 4 columns: kEmuPairs of every 8 element pairs go through
+      // the FMA pipes (ex2_fma2), the rest through the MUFU
+      auto exp4 = [&](int i, float nmc_) {
+        ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc_, nmc_);
+        ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc_, nmc_);
+        if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
+          ex2_fma2(s[i], s[i + 1]);
+        } else {
+          s[i] = ex2_approx(s[i]);
+          s[i + 1] = ex2_approx(s[i + 1]);
+        }
+        if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
+          ex2_fma2(s[i + 2], s[i + 3]);
+        } else {
+          s[i + 2] = ex2_approx(s[i + 2]);
+          s[i + 3] = ex2_approx(s[i + 3]);
+        }
+      };
+
+      // Columns [0,32) are exponentiated against the running max of the PREVIOUS tiles while the
+      // max of this tile is still being reduced (the MUFU is the busiest pipe: the max, the pair
+      // exchange and the packing run in its shadow).  That is exact whenever the lazy-rescale rule
+      // keeps m_run anyway (max grew by < 2^8); otherwise the slow path below redoes the columns.
+      float nmc = -m_run * c;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 4; i < 64; i += 4) {
-        mx0 = fmaxf(mx0, s[i]);
-        mx1 = fmaxf(mx1, s[i + 1]);
-        mx2 = fmaxf(mx2, s[i + 2]);
-        mx3 = fmaxf(mx3, s[i + 3]);
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
+        mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
+        mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
+        mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
+        exp4(i, nmc);
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       my_max[(j & 1) * 512] = mx;
       named_bar_sync(pair_bar, 64);
       const float m_cand = fmaxf(fmaxf(mx, other_max[(j & 1) * 512]), m_run);
       // both threads of the row see the same three numbers, so they take the same decision
+      const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
       float alpha = 1.f;
-      if ((m_cand - m_run) * c > kRescaleThreshold) {  // also true for the first tile (m_run = -inf)
-        alpha = ex2_approx((m_run - m_cand) * c);
-        m_run = m_cand;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        // rare (lazy rescale): O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was
-        // issued before S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
-#pragma unroll 1
-        for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
-          uint32_t o[8];
-          tmem_ld_x8(tO + c8, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x8(tO + c8, o);
+      if (__any_sync(0xffffffffu, grow)) {
+        // slow path (first tile; afterwards only when some row max grew by more than 2^8)
+        if (grow) {
+          alpha = ex2_approx((m_run - m_cand) * c);
+          m_run = m_cand;
         }
+        if (j > 0) {
+          // O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was issued before
+          // S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
+#pragma unroll 1
+          for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
+            uint32_t o[8];
+            tmem_ld_x8(tO + c8, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x8(tO + c8, o);
+          }
+        }
+        // redo columns [0,32) against the new max: S is still intact in TMEM (no P stored yet)
+        nmc = -m_run * c;
+        tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
+        tmem_wait_ld();
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= lim) s[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) exp4(i, nmc);
       }
       FA_TR(tr_role, j, 3);
-      // p = 2^(s*c - m*c), 32 columns at a time: exponentiate, round to 16 bit, store over S.
-      // kEmuPairs of every 8 element pairs go through the FMA pipes (ex2_fma2), the rest through
-      // the MUFU.  The row sum is taken after the hand-off (the MMA does not need it).
-      const float nmc = -m_run * c;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
+
+      // ---- first half of my P columns -> TMEM -> "early" hand-off
+      {
         uint32_t pk[16];
 #pragma unroll
-        for (int i = q * 32; i < q * 32 + 32; i += 4) {
-          ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc, nmc);
-          ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc, nmc);
-          if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
-            ex2_fma2(s[i], s[i + 1]);
-          } else {
-            s[i] = ex2_approx(s[i]);
-            s[i + 1] = ex2_approx(s[i + 1]);
-          }
-          if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
-            ex2_fma2(s[i + 2], s[i + 3]);
-          } else {
-            s[i + 2] = ex2_approx(s[i + 2]);
-            s[i + 3] = ex2_approx(s[i + 3]);
-          }
-          pk[(i - q * 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
-          pk[((i - q * 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
+        for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(s[2 * i], s[2 * i + 1]);
+        tmem_st_x16(tS, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_early(t));
+        FA_TR(tr_role, j, 4);
+      }
+      // ---- second half, with the row sum of the first half in the MUFU shadow
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 32; i < 64; i += 4) {
+          exp4(i, nmc);
+          fadd2(sum0, sum1, sum0, sum1, s[i - 32], s[i - 31]);
+          fadd2(sum2, sum3, sum2, sum3, s[i - 30], s[i - 29]);
+          pk[(i - 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
+          pk[((i - 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
         }
-        tmem_st_x16(tS + q * 16, pk);
+        tmem_st_x16(tS + 16, pk);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (q == 0) {
-            mbar_arrive(bar_p_early(t));
-          } else {
-            mbar_arrive(bar_p_late(t));
-            if (kSeq) mbar_arrive(bar_seq(t ^ 1));
-          }
+          mbar_arrive(bar_p_late(t));
+          if (kSeq) mbar_arrive(bar_seq(t ^ 1));
         }
-        FA_TR(tr_role, j, 4 + q);
+        FA_TR(tr_role, j, 5);
       }
-
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
+      for (int i = 32; i < 64; i += 4) {
         fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
         fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
       }
