@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,9 +89,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
+        """Summary of the samples that arrived inside ``window`` = (t0, t1) in perf_counter time
+        (all samples when None)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -102,7 +104,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if window is not None and not (window[0] <= ts <= window[1] + 0.03):
+                continue
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -202,19 +206,33 @@ def make_pool(shape, dtype, device, min_bytes):
 
 
 def time_variant(fa, pool, causal, iters, warm=3):
-    """Average device time (ms) of one forward on rotating inputs (extra sweeps, not the headline)."""
-    for i in range(warm):
-        q, k, v = pool[i % len(pool)]
-        fa(q, k, v, None, causal)
+    """Average device time (ms) of one forward on rotating inputs (extra sweeps, not the headline):
+    ``reps`` launches captured into a CUDA graph, replayed until ~``iters`` launches have run."""
+    reps = max(2, min(len(pool), 16))
+    side = torch.cuda.Stream()
+
+    def fn():
+        return [fa(*pool[i % len(pool)], None, causal) for i in range(reps)]
+
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        keep = fn()
+    g.replay()
+    torch.cuda.synchronize()
+    n_rep = max(1, iters // reps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        q, k, v = pool[i % len(pool)]
-        fa(q, k, v, None, causal)
+    for _ in range(n_rep):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    del keep
+    return e0.elapsed_time(e1) / (n_rep * reps)
 
 
 def main():
@@ -287,29 +305,106 @@ def main():
             fa(q, k, v, None, False)
     torch.cuda.synchronize()
 
+    # ---- capture.  The forward at N <= 2048 lasts a few microseconds, less than the Python +
+    # ctypes cost of one FlashAttentionFunction.apply, so an eager loop would time the host.  The K
+    # steps (K x len(points) launches through the public entry point, rotating inputs) are captured
+    # once into a CUDA graph and the timed region replays it: same kernels, same arguments.
+    side = torch.cuda.Stream(device=dev)
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()  # allocator + plan-cache warm-up on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            outs = fn()
+        return g, outs
+
+    def k_steps():
+        outs = []
+        for s_ in range(args.steps):
+            for (b, n) in points:
+                q, k, v = pools[n][(args.warmup + s_) % len(pools[n])]
+                outs.append(fa(q, k, v, None, False))
+        return outs
+
+    launches0 = _capi.launch_count()
+    graph_all, keep_all = capture(k_steps)
+    launches = (_capi.launch_count() - launches0) // 2  # captured once after one eager warm-up pass
+
+    # per-sequence-length graphs (for the per-N table and the roofline of the dominant kernel)
+    per_graphs = {}
+    for (b, n) in points:
+        reps = max(4, min(len(pools[n]), 32))
+
+        def one_n(n=n, reps=reps):
+            return [fa(*pools[n][i % len(pools[n])], None, False) for i in range(reps)]
+
+        per_graphs[n] = (capture(one_n), reps)
+
+    graph_all.replay()  # one untimed replay
+    torch.cuda.synchronize()
+
     # ---- timed region: EXACTLY K steps, events on the launching (current) stream
-    n_ev = len(points) + 1
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(n_ev)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.1)
     barrier()
-    launches0 = _capi.launch_count()
-    for s in range(args.steps):
-        ev = events[s]
-        ev[0].record()
-        for i, (b, n) in enumerate(points):
-            q, k, v = pools[n][(args.warmup + s) % len(pools[n])]
-            fa(q, k, v, None, False)
-            ev[i + 1].record()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    graph_all.replay()
+    e1.record()
     barrier()
-    launches = _capi.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.perf_counter()
+    total_ms = e0.elapsed_time(e1)
 
-    total_ms = events[0][0].elapsed_time(events[-1][-1])
-    per_point_ms = [sum(events[s][i].elapsed_time(events[s][i + 1]) for s in range(args.steps)) / args.steps
-                    for i in range(len(points))]
+    per_point_ms = []
+    for (b, n) in points:
+        (g, _keep), reps = per_graphs[n]
+        g.replay()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(3):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            g.replay()
+            a1.record()
+            torch.cuda.synchronize()
+            best = min(best, a0.elapsed_time(a1) / reps)
+        per_point_ms.append(best)
+
+    # clocks: the timed region can be shorter than one nvidia-smi period, so keep replaying the same
+    # graph (untimed) for ~0.4 s and report the clocks of both windows
+    clocks = None
+    if rank == 0:
+        t_probe0 = time.perf_counter()
+        while time.perf_counter() - t_probe0 < 0.4:
+            graph_all.replay()
+            torch.cuda.synchronize()
+        t_probe1 = time.perf_counter()
+        timed = sampler.stop(window=(t_wall0, t_wall1))
+        probe = sampler.stop(window=(t_probe0, t_probe1))
+        clocks = probe if not timed.get("samples") else timed
+        clocks["window"] = "sustained probe (0.4 s of the same graph)" if not timed.get("samples") else "timed region"
+        clocks["sustained_probe"] = {k: probe.get(k) for k in ("sm_mhz", "samples", "reasons")}
+        clocks["reasons"] = sorted(set(timed.get("reasons", [])) | set(probe.get("reasons", [])))
+
+    # eager loop through the same entry point, for the record (host-bound at small N)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for s_ in range(args.steps):
+        for (b, n) in points:
+            q, k, v = pools[n][(args.warmup + s_) % len(pools[n])]
+            fa(q, k, v, None, False)
+    ev1.record()
+    torch.cuda.synchronize()
+    eager_ms_per_step = ev0.elapsed_time(ev1) / args.steps
+
     if dist is not None:
         t = torch.tensor([total_ms] + per_point_ms, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,6 +458,9 @@ def main():
                    "heads": H, "head_dim": D, "seqlens": [n for (_, n) in points],
                    "parallelism": f"batch-shard x{world} (no collective)",
                    "l2": "rotating input pools > 2x L2 (252 MiB) per sequence length",
+                   "launch": "the K steps are captured once into a CUDA graph (through "
+                             "FlashAttentionFunction.apply) and the timed region replays it",
+                   "eager_ms_per_step": round(eager_ms_per_step, 5),
                    "per_n": per_n},
         "roofline": roofline,
         "gpu_launches": int(launches),

@@ -149,8 +149,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t tx_
                : "memory");
 }
 
+// FA_TRY_WAIT_HINT_NS: suspend-time hint of mbarrier.try_wait.  A waiting thread sleeps in hardware
+// until the phase completes or the hint expires instead of returning to the polling loop every few
+// dozen cycles.  Measured on B200 (tools/ab_bench.py): 0x989680 (the value CUTLASS uses) is 1-2 % SLOWER
+// than plain polling for this kernel, burst and sustained, so the default is 0 = no hint.
+#ifndef FA_TRY_WAIT_HINT_NS
+#define FA_TRY_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if FA_TRY_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(FA_TRY_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -160,6 +178,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 
