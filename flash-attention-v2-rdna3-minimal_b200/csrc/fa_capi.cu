@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/fa_fwd_sm100.h"
+#include "fa_bwd_tc.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
@@ -325,6 +326,46 @@ int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse
   return FA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward launchers
+// ---------------------------------------------------------------------------------------------
+struct BwdMaps {
+  CUtensorMap q, k, v, d_o, dk, dv;
+};
+
+template <int kDP, bool kBF16, bool kCausal>
+int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
+                  cudaStream_t stream) {
+  auto kernel = fa::fa_bwd_tc_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::BwdSmem<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, device);
+  if (rc) return rc;
+  dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
+  kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, bp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+int dispatch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int D, int dtype,
+                    int causal, int device, cudaStream_t stream) {
+  const bool bf = dtype == FA_DTYPE_BF16;
+  const bool ca = causal != 0;
+#define FA_BWD_DISPATCH(DP)                                                                    \
+  do {                                                                                         \
+    if (bf) {                                                                                  \
+      if (ca) return launch_bwd_tc<DP, true, true>(m, bp, B, H, Nkv, device, stream);          \
+      return launch_bwd_tc<DP, true, false>(m, bp, B, H, Nkv, device, stream);                 \
+    }                                                                                          \
+    if (ca) return launch_bwd_tc<DP, false, true>(m, bp, B, H, Nkv, device, stream);           \
+    return launch_bwd_tc<DP, false, false>(m, bp, B, H, Nkv, device, stream);                  \
+  } while (0)
+  if (D <= 64) FA_BWD_DISPATCH(64);
+  FA_BWD_DISPATCH(128);
+#undef FA_BWD_DISPATCH
+}
+
 int check_device(int* device_out) {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
@@ -563,6 +604,84 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
   return FA_OK;
 }
 
+int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                 const float* lse, void* dq, void* dk, void* dv, float* dq_accum, float* delta, int B,
+                 int H, int Nq, int Nkv, int D, const int64_t q_strides[4],
+                 const int64_t k_strides[4], const int64_t v_strides[4], const int64_t o_strides[4],
+                 const int64_t do_strides[4], const int64_t dq_strides[4],
+                 const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, int causal,
+                 float scale, void* stream) {
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr || d_o == nullptr ||
+      lse == nullptr || dq == nullptr || dk == nullptr || dv == nullptr || dq_accum == nullptr ||
+      delta == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "fa_bwd_sm100: every buffer pointer must be non-null");
+  if (do_strides == nullptr || dq_strides == nullptr || dk_strides == nullptr || dv_strides == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "stride arrays must not be null");
+  Problem p{};
+  p.B = B; p.H = H; p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype; p.causal = causal;
+  p.scale = scale;
+  int rc = validate(p, q_strides, k_strides, v_strides, o_strides);
+  if (rc) return rc;
+  int64_t dos[4], dqs[4], dks[4], dvs[4];
+  memcpy(dos, do_strides, sizeof dos);
+  memcpy(dqs, dq_strides, sizeof dqs);
+  memcpy(dks, dk_strides, sizeof dks);
+  memcpy(dvs, dv_strides, sizeof dvs);
+  if (dos[3] != 1 || dqs[3] != 1 || dks[3] != 1 || dvs[3] != 1)
+    return fail(FA_ERR_INVALID_ARG, "the innermost (head-dim) stride of dO, dQ, dK and dV must be 1");
+  canon_strides(dos, B, H, Nq, D);
+  canon_strides(dqs, B, H, Nq, D);
+  canon_strides(dks, B, H, Nkv, D);
+  canon_strides(dvs, B, H, Nkv, D);
+  const bool tc = (D % 8 == 0) && (D <= 128) && tma_ok_strides(p.qs) && tma_ok_strides(p.ks) &&
+                  tma_ok_strides(p.vs) && tma_ok_strides(dos) && tma_ok_strides(dks) &&
+                  tma_ok_strides(dvs) && aligned16(q) && aligned16(k) && aligned16(v) &&
+                  aligned16(d_o) && aligned16(dk) && aligned16(dv) && aligned16(dq_accum);
+  if (!tc)
+    return fail(FA_ERR_UNSUPPORTED,
+                "fa_bwd_sm100 needs head dim % 8 == 0 and <= 128 with 16-byte aligned pointers and "
+                "strides (pad the head dim in the caller, as FlashAttn.py does)");
+  int dev;
+  if ((rc = check_device(&dev))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int64_t rows = int64_t(B) * H * Nq;
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  // 1. delta = rowsum(dO o O), dq_accum = 0
+  if (dtype == FA_DTYPE_BF16)
+    fa::fa_bwd_delta_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta, dq_accum,
+        B, H, Nq, D, D, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
+  else
+    fa::fa_bwd_delta_kernel<__half><<<blocks, 256, 0, st>>>(
+        static_cast<const __half*>(o), static_cast<const __half*>(d_o), delta, dq_accum, B, H, Nq, D,
+        D, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+
+  // 2. main kernel
+  BwdMaps m;
+  if ((rc = make_map(&m.q, q, B, H, Nq, D, p.qs, dtype, fa::kTileM))) return rc;
+  if ((rc = make_map(&m.k, k, B, H, Nkv, D, p.ks, dtype, fa::kTileN))) return rc;
+  if ((rc = make_map(&m.v, v, B, H, Nkv, D, p.vs, dtype, fa::kTileN))) return rc;
+  if ((rc = make_map(&m.d_o, d_o, B, H, Nq, D, dos, dtype, fa::kTileM))) return rc;
+  if ((rc = make_map(&m.dk, dk, B, H, Nkv, D, dks, dtype, fa::kTileN))) return rc;
+  if ((rc = make_map(&m.dv, dv, B, H, Nkv, D, dvs, dtype, fa::kTileN))) return rc;
+  fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale};
+  if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
+
+  // 3. dQ = scale * dq_accum
+  if (dtype == FA_DTYPE_BF16)
+    fa::fa_bwd_dq_convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        dq_accum, static_cast<__nv_bfloat16*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
+  else
+    fa::fa_bwd_dq_convert_kernel<__half><<<blocks, 256, 0, st>>>(
+        dq_accum, static_cast<__half*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 int fa_host_workspace_release(void) {
   int dev;
   int rc = check_device(&dev);
@@ -576,7 +695,7 @@ int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mo
                      uint32_t sbo, void* stream) {
   if (a == nullptr || b == nullptr || out == nullptr)
     return fail(FA_ERR_INVALID_ARG, "a, b and out must not be null");
-  if (mode < 0 || mode > 3) return fail(FA_ERR_INVALID_ARG, "mode must be 0..3");
+  if (mode < 0 || mode > 4) return fail(FA_ERR_INVALID_ARG, "mode must be 0..4");
   if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
     return fail(FA_ERR_INVALID_ARG, "dtype must be FA_DTYPE_F16 or FA_DTYPE_BF16");
   int dev;

@@ -7,6 +7,7 @@
 //   mode 1  D = A * B     A K-major via TMA, B MN-major via TMA         -> the O = P V path (SS)
 //   mode 2  D = A * B     A packed into TMEM by tcgen05.st, B MN-major  -> the O = P V path (TS)
 //   mode 3  D = A * B     A written to smem by threads (manual swizzle) -> P-through-smem variant
+//   mode 4  D = A^T * B   A MN-major (stored [k][m]), B MN-major        -> dV = P^T dO, dK = dS^T Q
 #pragma once
 #include "ptx.cuh"
 
@@ -53,7 +54,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem = *tmem_slot;
 
   if (tid == 0) {
-    const bool a_tma = (mode == 0 || mode == 1);
+    const bool a_tma = (mode == 0 || mode == 1 || mode == 4);
     mbar_arrive_expect_tx(bar_load, a_tma ? 65536 : 32768);
     if (a_tma) {
       tma_load_4d(smem_u32(sA), &tmap_a, bar_load, 0, 0, 0, 0);
@@ -94,11 +95,12 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_after();
     const uint32_t a_base = smem_u32(sA);
     const uint32_t b_base = smem_u32(sB);
-    const uint32_t idesc = make_idesc_f16(128, 128, kBF16, false, mode != 0);
+    const uint32_t idesc = make_idesc_f16(128, 128, kBF16, mode == 4, mode != 0);
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
       const uint32_t a_addr = a_base + (k >> 2) * 16384 + (k & 3) * 32;
-      const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
+      const uint64_t a_desc = (mode == 4) ? make_smem_desc_sw128(a_base + k * 2048, lbo_b, sbo_b)
+                                          : make_smem_desc_sw128(a_addr, 16, 1024);
       uint64_t b_desc;
       if (mode == 0) {
         b_desc = make_smem_desc_sw128(b_base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);

@@ -1,4 +1,4 @@
-"""Drop-in for the forward path of /root/reference/rocwmma_fattn/FlashAttn.py.
+"""Drop-in for /root/reference/rocwmma_fattn/FlashAttn.py (forward, and backward for head dims <= 128).
 
 Same entry point and calling convention as the reference::
 
@@ -112,6 +112,41 @@ def _forward(q, k, v, causal, scale, bnhd, want_lse):
     return o, lse, (qp, kp, vp, o_full), (causal, float(scale), Nq, Nkv, D, bnhd)
 
 
+def _backward(qp, kp, vp, o_full, d_o, lse, D, causal, scale, bnhd):
+    """dQ, dK, dV on the tensors the forward saved (head dim padded to a multiple of 8).  Replaces
+    backward_fp16 / backward_bf16 (kernel_fp16.cu:878-1028): the incoming gradient is zero-padded
+    in the head dim like there (:903-917), the three gradients come back sliced to ``D``."""
+    if not qp.is_cuda:
+        raise RuntimeError("rocwmma_fattn (B200 build) runs on CUDA tensors only; there is no CPU fallback")
+    DP = qp.shape[3]
+    if DP > _TC_MAX_D or DP % _TMA_D_ALIGN:
+        raise NotImplementedError(
+            f"the sm_100a backward kernel covers head dims up to {_TC_MAX_D} (got {D}); larger head "
+            "dims run forward-only in this build")
+    if d_o.dtype != qp.dtype:
+        d_o = d_o.to(qp.dtype)  # host.cpp:49-57 dispatches on dO's dtype; ours follows q's
+    d_o = _prepare(d_o, DP - d_o.shape[3])
+    B, H, Nq, _ = _logical_shape(qp, bnhd)
+    Nkv = _logical_shape(kp, bnhd)[2]
+    dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
+    dq_acc = torch.empty((B, H, Nq, DP), dtype=torch.float32, device=qp.device)
+    delta = torch.empty((B, H, Nq), dtype=torch.float32, device=qp.device)
+    st = lambda t: _capi.strides4(_logical_strides(t, bnhd))  # noqa: E731
+    with torch.cuda.device(qp.device):
+        stream = torch.cuda.current_stream(qp.device).cuda_stream
+        rc = _capi.lib.fa_bwd_sm100(
+            qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), o_full.data_ptr(), d_o.data_ptr(),
+            lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dq_acc.data_ptr(),
+            delta.data_ptr(), B, H, Nq, Nkv, DP,
+            st(qp), st(kp), st(vp), st(o_full), st(d_o), st(dq), st(dk), st(dv),
+            _dtype_code(qp.dtype), int(causal), float(scale), stream,
+        )
+    _capi.check(rc, "fa_bwd_sm100")
+    if DP != D:
+        dq, dk, dv = dq[..., :D], dk[..., :D], dv[..., :D]
+    return dq, dk, dv
+
+
 def flash_attn_forward(q, k, v, causal=False, scale=None, BNHD_fmt=False, return_lse=False):
     """Functional form of the forward.  With ``return_lse`` also returns the base-2 log-sum-exp of
     the scaled scores, fp32 ``[B,H,Nq]`` (what the reference stores in ``L``,
@@ -162,12 +197,11 @@ class _NativeModule:
         return [o, qp, kp, vp, o_full, lse]
 
     @staticmethod
-    def backward(*args, **kwargs):
-        raise NotImplementedError(
-            "the B200 build implements the forward path only (SURVEY.md section 8f ranks the "
-            "backward kernel as the next component); use the saved (q, k, v, o, L) with your own "
-            "backward or torch SDPA for training"
-        )
+    def backward(Q, K, V, O, dO, L, act_n, act_nkv, act_d, Br, Bc, causal, scale, permute_NH):
+        """Reference signature (host.cpp:9-22,47-58): the tensors saved by ``forward`` (head dim
+        already padded), the incoming gradient, the actual sizes, the tile sizes (ignored) -> the
+        three gradients sliced to ``act_d`` (kernel_fp16.cu:1000-1027)."""
+        return list(_backward(Q, K, V, O, dO, L, act_d, bool(causal), float(scale), bool(permute_NH)))
 
 
 flash_attn_wmma = _NativeModule()
@@ -190,4 +224,8 @@ class FlashAttentionFunction(torch.autograd.Function):
     @staticmethod
     @torch.no_grad()
     def backward(ctx, do):
-        return flash_attn_wmma.backward(ctx, do)
+        """Reference: FlashAttn.py:80-92 (Br = Bc = 128 there; tile sizes are internal here)."""
+        causal, scale, mask, N, Nkv, D, bnhd = ctx.args
+        q, k, v, o, L = ctx.saved_tensors
+        dQ, dK, dV = flash_attn_wmma.backward(q, k, v, o, do, L, N, Nkv, D, 128, 128, causal, scale, bnhd)
+        return dQ, dK, dV, None, None, None, None

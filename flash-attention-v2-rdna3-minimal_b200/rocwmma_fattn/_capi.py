@@ -14,7 +14,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # FA_FWD_SM100_LIB selects another build of the same C-ABI (e.g. the FA_TRACE debug library)
 LIB_PATH = os.environ.get("FA_FWD_SM100_LIB") or os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
 
-FA_ABI_VERSION = 1
+FA_ABI_VERSION = 2
 FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
 FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0, 1, 2, 3, 4
 FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS = 0, 1, 2, 3, 4
@@ -30,6 +30,7 @@ KERNEL_NAMES = {
 EXPORTED_SYMBOLS = (
     "fa_fwd_sm100",
     "fa_fwd_sm100_host",
+    "fa_bwd_sm100",
     "fa_host_workspace_release",
     "fa_last_error",
     "fa_abi_version",
@@ -61,6 +62,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_fwd_sm100.restype = i
     lib.fa_fwd_sm100_host.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f]
     lib.fa_fwd_sm100_host.restype = i
+    lib.fa_bwd_sm100.argtypes = [vp] * 11 + [i] * 5 + [p64] * 8 + [i, i, f, vp]
+    lib.fa_bwd_sm100.restype = i
     lib.fa_host_workspace_release.argtypes = []
     lib.fa_host_workspace_release.restype = i
     lib.fa_last_error.argtypes = []

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FA_ABI_VERSION 1
+#define FA_ABI_VERSION 2
 
 /* element types (reference: host.cpp:32-44 dispatches on torch::kFloat16 / torch::kBFloat16) */
 #define FA_DTYPE_F16 0
@@ -85,6 +85,34 @@ int fa_fwd_sm100(const void* q, const void* k, const void* v, void* o, float* ls
 int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, float* lse, int B,
                       int H, int Nq, int Nkv, int D, int dtype, int causal, float scale);
 
+/*
+ * Attention backward on device buffers.  Replaces host.cpp:47-58 `backward` + kernel_*.cu
+ * `backward_fp16/bf16` (kernel_fp16.cu:878-1028, kernel_bf16.cu:943-1092) and `bwd_kernel`
+ * (kernel_fp16.cu:547-740).
+ *
+ *   q, k, v, o   the forward's inputs and output (o: [B,H,Nq,D], strides o_strides)
+ *   d_o          gradient of the loss w.r.t. o, [B,H,Nq,D] logical, strides do_strides
+ *   lse          the forward's base-2 log-sum-exp, contiguous fp32 [B,H,Nq] (fa_fwd_sm100 `lse`)
+ *   dq, dk, dv   outputs, shaped / typed like q, k, v; strides dq_strides / dk_strides / dv_strides
+ *   dq_accum     caller-owned fp32 workspace, contiguous [B,H,Nq,D] (zeroed here); dQ is accumulated
+ *                across key tiles with fp32 atomics - the reference adds into a 16-bit dQ from
+ *                several CTAs without atomics (kernel_fp16.cu:736)
+ *   delta        caller-owned fp32 workspace, contiguous [B,H,Nq]; receives rowsum(dO o O)
+ *                (what the reference recomputes in every CTA, kernel_fp16.cu:605-631)
+ *
+ * Tensor-core path only: D % 8 == 0, D <= 128, 16-byte aligned pointers and strides, innermost
+ * strides 1; anything else returns FA_ERR_UNSUPPORTED (the Python layer pads the head dim exactly
+ * as the reference's launcher does, kernel_fp16.cu:903-917).  Three launches (pre-pass, main kernel,
+ * dQ conversion) on `stream`, asynchronous with respect to the host.
+ */
+int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                 const float* lse, void* dq, void* dk, void* dv, float* dq_accum, float* delta, int B,
+                 int H, int Nq, int Nkv, int D, const int64_t q_strides[4],
+                 const int64_t k_strides[4], const int64_t v_strides[4], const int64_t o_strides[4],
+                 const int64_t do_strides[4], const int64_t dq_strides[4],
+                 const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, int causal,
+                 float scale, void* stream);
+
 /* Release the device workspace and streams fa_fwd_sm100_host() caches for the current device. */
 int fa_host_workspace_release(void);
 
@@ -112,7 +140,8 @@ uint64_t fa_launch_count(void);
 /*
  * UMMA / TMA / TMEM self-test: computes one 128x128x128 product through the same operand paths the
  * attention kernels use (mode 0: A.B^T both K-major; 1: A.B with B MN-major; 2: A from TMEM;
- * 3: A written to smem by threads).  a, b: device [128,128] 16-bit row-major; out: device
+ * 3: A written to smem by threads; 4: A^T.B with A and B MN-major, the backward's dV/dK products).
+ * a, b: device [128,128] 16-bit row-major; out: device
  * [128,128] fp32.  lbo/sbo: B-descriptor byte offsets for modes 1-3 (0,0 = the values the kernels
  * use).  Counterpart of the reference's gemm_test/ micro-kernels.
  */

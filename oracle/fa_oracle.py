@@ -15,6 +15,9 @@ It restates, on the CPU, the algorithm of the reference's own oracle and checker
                             path" that bench.py times as ``cpu_baseline``
 * ``lse_base2``          <- /root/reference/rocwmma_fattn/kernel_fp16.cu:541-542 (L = m + log2 l over
                             scores pre-multiplied by scale*log2(e), :827)
+* ``tiled_fa2_backward`` <- /root/reference/pure_torch_ver.py:94-153  (tiled FA2 backward)
+* ``sdpa_backward``      <- autograd through math SDPA, the reference's gradient check
+                            (pure_torch_ver.py:192-205, precision_test.py:75-98)
 
 Pinning: the reference ships no golden vectors, tolerances or seeds, so the
 oracle is pinned against outputs of the reference's own ``pure_torch_ver.py`` run in the build
@@ -146,6 +149,84 @@ def tiled_fa2_forward(q, k, v, causal=False, Br=64, Bc=256):
     return o[:, :, :N, :], L[:, :, :N]
 
 
+def sdpa_backward(q, k, v, d_o, causal=False, scale=None, dtype=torch.float32):
+    """Ground truth for the backward: autograd through the math definition
+    softmax(scale q k^T [+ causal mask]) v evaluated in ``dtype`` (what the reference's
+    ``o2.backward(dO)`` on math-SDPA gives, pure_torch_ver.py:192-205 / precision_test.py:75-98).
+    Returns (dq, dk, dv) in ``dtype``."""
+    qf = q.detach().to(dtype).requires_grad_(True)
+    kf = k.detach().to(dtype).requires_grad_(True)
+    vf = v.detach().to(dtype).requires_grad_(True)
+    d = q.shape[-1]
+    if scale is None:
+        scale = d ** -0.5
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if causal:
+        keep = _causal_keep_mask(q.shape[-2], k.shape[-2], device=q.device)
+        s = s.masked_fill(~keep, float("-inf"))
+    o = torch.matmul(torch.softmax(s, dim=-1), vf)
+    o.backward(d_o.to(dtype))
+    return qf.grad, kf.grad, vf.grad
+
+
+def tiled_fa2_backward(q, k, v, o, L, d_o, causal=False, Br=64, Bc=256):
+    """Restatement of the reference oracle's backward (pure_torch_ver.py:94-153) for sequence
+    lengths that are multiples of the tile sizes, arithmetic in the input dtype:
+
+      for each Bc-row K/V tile j, for each Br-row Q tile i:
+        S = scale Q_i K_j^T, causal fill -inf above the diagonal            (:137-144)
+        P = exp(S - L_i) rounded to the input dtype                          (:146)
+        dV_j += P^T dO_i;  dP = dO_i V_j^T;  D_i = rowsum(dO_i o O_i)        (:147-149)
+        dS = scale P (dP - D_i);  dQ_i += dS K_j;  dK_j += dS^T Q_i          (:150-152)
+
+    ``L`` is the natural-log LSE the oracle forward returns.  Returns (dq, dk, dv)."""
+    B, H, N, D = q.shape
+    Nkv = k.shape[-2]
+    if N % Br or Nkv % Bc:
+        raise ValueError("tiled_fa2_backward restates the aligned case only")
+    scale = D ** -0.5
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    for c0 in range(0, Nkv, Bc):
+        kj, vj = k[:, :, c0:c0 + Bc, :], v[:, :, c0:c0 + Bc, :]
+        for r0 in range(0, N, Br):
+            qi, oi, doi = q[:, :, r0:r0 + Br, :], o[:, :, r0:r0 + Br, :], d_o[:, :, r0:r0 + Br, :]
+            li = L[:, :, r0:r0 + Br]
+            s = scale * torch.matmul(qi, kj.transpose(-1, -2))
+            if causal and r0 < c0 + Bc - 1:
+                rows = torch.arange(r0, r0 + Br).unsqueeze(1)
+                cols = torch.arange(c0, c0 + Bc).unsqueeze(0)
+                s = s.masked_fill(cols > rows, float("-inf"))
+            p = torch.exp(s - li.unsqueeze(-1)).to(q.dtype)
+            dv[:, :, c0:c0 + Bc, :] += torch.matmul(p.transpose(-1, -2), doi)
+            dp = torch.matmul(doi, vj.transpose(-1, -2))
+            di = torch.sum(doi * oi, -1)
+            ds = scale * p * (dp - di.unsqueeze(-1))
+            dq[:, :, r0:r0 + Br, :] += torch.matmul(ds, kj)
+            dk[:, :, c0:c0 + Bc, :] += torch.matmul(ds.transpose(-1, -2), qi)
+    return dq, dk, dv
+
+
+# Backward gate.  Ground truth = fp32 autograd of math SDPA (``sdpa_backward``).  Every Flash-
+# Attention backward, the reference's included, takes D_i = rowsum(dO o O) from the 16-bit O the
+# forward stored (kernel_fp16.cu:605-631), so part of its distance from fp32 autograd is inherited
+# from that rounding, not from the backward arithmetic (dQ of uniform data is a heavily cancelling
+# sum: 1 % of max|dQ| in fp16, 13 % in bf16 at N = 512 for ANY implementation).  The gate is the
+# reference's own procedure made quantitative: precision_test.py:65-98 compares the extension with
+# math SDPA run in the SAME 16-bit dtype; we require
+#     max|g - ref32| <= 2 * max|g16 - ref32| + 1e-5 + 1e-3 * max|ref32|
+# where g16 = autograd of math SDPA evaluated in the 16-bit input dtype (``sdpa_backward(dtype=...)``),
+# i.e. at most twice the error of the plain 16-bit PyTorch implementation (the criterion the public
+# flash-attention test-suite uses), and the tests on the committed fixtures also require the
+# kernels to be at least as close to fp32 as the reference's tiled oracle is.
+def check_close_grad(g, ref_fp32, g16) -> tuple[bool, float, float]:
+    """Returns (ok, err, bound) for one gradient tensor; ``g16`` is the 16-bit baseline gradient."""
+    r64 = ref_fp32.double().cpu()
+    err = (g.double().cpu() - r64).abs().max().item()
+    base = (g16.double().cpu() - r64).abs().max().item()
+    bound = 2.0 * base + 1e-5 + 1e-3 * r64.abs().max().item()
+    return err <= bound, err, bound
+
+
 def attention_flops(B, H, Nq, Nkv, D, causal=False) -> float:
     """The reference's FLOP count: 2 matmuls x 2 B H N^2 D, halved when causal
     (bench_with_sdpa.py:35-38)."""
@@ -192,6 +273,7 @@ def nan_free(t: torch.Tensor) -> bool:
 
 __all__ = [
     "sdpa_math", "lse_base2", "cpu_sdpa", "tiled_fa2_forward", "attention_flops",
+    "sdpa_backward", "tiled_fa2_backward", "check_close_grad",
     "attention_bytes", "make_inputs", "max_abs_err", "check_close", "nan_free",
     "TOL_VS_FP32", "LOG2E",
 ]

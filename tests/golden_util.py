@@ -8,8 +8,18 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_names():
+def _names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Forward fixtures (tests/golden/make_golden.py)."""
+    return [n for n in _names() if not n.startswith("bwd_")]
+
+
+def golden_bwd_names():
+    """Backward fixtures (tests/golden/make_golden_bwd.py)."""
+    return [n for n in _names() if n.startswith("bwd_")]
 
 
 def _from_bits(a: np.ndarray, dtype: torch.dtype) -> torch.Tensor:
@@ -25,4 +35,18 @@ def load_golden(name: str) -> dict:
     out["causal"] = bool(z["causal"])
     out["seed"] = int(z["seed"])
     out["dist"] = str(z["dist"])
+    return out
+
+
+def load_golden_bwd(name: str) -> dict:
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    dtype = torch.float16 if str(z["dtype"]) == "float16" else torch.bfloat16
+    out = {k: _from_bits(z[k], dtype) for k in ("q", "k", "v", "d_o", "o_ref_tiled", "dq_ref_tiled",
+                                                "dk_ref_tiled", "dv_ref_tiled", "dq_sdpa16", "dk_sdpa16",
+                                                "dv_sdpa16")}
+    for k in ("dq_f32", "dk_f32", "dv_f32"):
+        out[k] = torch.from_numpy(z[k].copy())
+    out["dtype"] = dtype
+    out["causal"] = bool(z["causal"])
+    out["seed"] = int(z["seed"])
     return out

@@ -68,6 +68,14 @@ def test_host_path_fails_loudly_without_gpu():
         FlashAttn.flash_attn_forward_host(h, h, h)
 
 
-def test_backward_entry_is_explicit():
-    with pytest.raises(NotImplementedError):
-        FlashAttn.flash_attn_wmma.backward()
+def test_backward_entry_has_the_reference_signature_and_no_cpu_fallback():
+    """host.cpp:9-22: backward(Q,K,V,O,dO,L,act_n,act_nkv,act_d,Br,Bc,causal,scale,permute_NH)."""
+    import inspect
+
+    names = list(inspect.signature(FlashAttn.flash_attn_wmma.backward).parameters)
+    assert names == ["Q", "K", "V", "O", "dO", "L", "act_n", "act_nkv", "act_d", "Br", "Bc", "causal",
+                     "scale", "permute_NH"]
+    t = torch.zeros(1, 1, 8, 8, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FlashAttn.flash_attn_wmma.backward(t, t, t, t, t, torch.zeros(1, 1, 8), 8, 8, 8, 128, 128, False,
+                                           0.35, False)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import fa_oracle as orc
-from golden_util import golden_names, load_golden
+from golden_util import golden_bwd_names, golden_names, load_golden, load_golden_bwd
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -90,3 +90,39 @@ def test_flop_and_byte_counts_match_baseline_table():
     assert orc.attention_flops(1, 16, 4096, 4096, 128, causal=True) == pytest.approx(0.5 * 1.374e11, rel=1e-3)
     assert orc.attention_bytes(1, 16, 512, 512, 128) == 16384 * 512
     assert orc.attention_flops(1, 2, 128, 128, 64) == pytest.approx(8.39e6, rel=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# backward oracle (pure_torch_ver.py:94-153) against the reference-generated fixtures
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_bwd_names())
+def test_backward_ground_truth_matches_stored_fp32_autograd(name):
+    g = load_golden_bwd(name)
+    dq, dk, dv = orc.sdpa_backward(g["q"], g["k"], g["v"], g["d_o"], causal=g["causal"])
+    for a, b in ((dq, g["dq_f32"]), (dk, g["dk_f32"]), (dv, g["dv_f32"])):
+        assert orc.max_abs_err(a, b) <= 1e-5 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("name", golden_bwd_names())
+def test_tiled_backward_restatement_matches_reference_tiled_oracle(name):
+    """oracle.tiled_fa2_backward restates pure_torch_ver.py:94-153 in the same 16-bit arithmetic: it
+    must land within a few ulps (of the largest entry) of what the reference's oracle produced."""
+    g = load_golden_bwd(name)
+    o, L = orc.tiled_fa2_forward(g["q"], g["k"], g["v"], causal=g["causal"])
+    dq, dk, dv = orc.tiled_fa2_backward(g["q"], g["k"], g["v"], o, L.to(g["dtype"]), g["d_o"], causal=g["causal"])
+    ulp = 2.0 ** -10 if g["dtype"] == torch.float16 else 2.0 ** -7
+    for nm, a, b in (("dq", dq, g["dq_ref_tiled"]), ("dk", dk, g["dk_ref_tiled"]), ("dv", dv, g["dv_ref_tiled"])):
+        assert orc.max_abs_err(a, b) <= 8 * ulp * b.float().abs().max().item() + 1e-4, nm
+
+
+@pytest.mark.parametrize("name", golden_bwd_names())
+def test_backward_16bit_baseline_reproducible_and_gate_admits_it(name):
+    """The 16-bit math-SDPA gradients the gate is built on are reproducible here, and the gate
+    trivially admits them (so it is never tighter than plain PyTorch is to fp32)."""
+    g = load_golden_bwd(name)
+    got = orc.sdpa_backward(g["q"], g["k"], g["v"], g["d_o"], causal=g["causal"], dtype=g["dtype"])
+    for nm, a in zip(("dq", "dk", "dv"), got):
+        b, r = g[nm + "_sdpa16"], g[nm + "_f32"]
+        assert orc.max_abs_err(a, b) <= 4e-3 * r.abs().max().item() + 1e-6, nm
+        ok, err, bound = orc.check_close_grad(b, r, b)
+        assert ok, (nm, err, bound)
