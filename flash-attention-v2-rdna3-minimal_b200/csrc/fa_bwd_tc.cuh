@@ -7,7 +7,7 @@
 // (:724), dP = dO V^T (:725), dS = P o (dP - D) (:732), dQ += dS K (:736), dK += dS^T Q (:737) -
 // with three deliberate differences:
 //   * the five products run on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM);
-//   * dQ is accumulated across K/V tiles in an fp32 buffer with red.global.add (the reference adds
+//   * dQ is accumulated across K/V tiles in an fp32 buffer with TMA reduce-add (the reference adds
 //     into an fp16 dQ from different CTAs without atomics, kernel_fp16.cu:736 - a data race);
 //   * D_i is computed once by a small pre-pass instead of by every CTA.
 //
@@ -18,7 +18,7 @@
 //   dV += P^T  dO_i         SS MMA, A = P  MN-major, B = dO MN-major     -> TMEM [256,256+D)
 //   dK += dS^T Q_i          SS MMA, A = dS MN-major, B = Q  MN-major     -> TMEM [384,384+D)
 //   dQ_i = dS K_j           SS MMA, A = dS K-major,  B = K  MN-major     -> TMEM [0,D) (over S)
-//   dQ_i: TMEM -> registers -> red.global.add.v4.f32 into dq_acc
+//   dQ_i: TMEM -> registers -> swizzled fp32 staging -> TMA reduce-add (cp.reduce.async.bulk) into dq_acc
 // One elected thread issues the TMA loads and every MMA; this first version is a serial pipeline
 // (the tensor cores idle during the P/dS pass and the dQ drain).
 #pragma once
@@ -45,7 +45,8 @@ struct BwdSmem {
   static constexpr int kdO = kQ + kTileBytes;
   static constexpr int kP = kdO + kTileBytes;            // [128 q][128 keys] 16 bit; dV staging
   static constexpr int kdS = kP + kTileM * kTileN * 2;    // [128 q][128 keys] 16 bit; dK staging
-  static constexpr int kBars = kdS + kTileM * kTileN * 2;
+  static constexpr int kStage = kdS + kTileM * kTileN * 2;  // 2 x [128 rows][32 fp32] dQ staging
+  static constexpr int kBars = kStage + 2 * kTileM * 128;
   static constexpr int kTotal = kBars + 128 + 1024;       // + alignment slack
 };
 
@@ -108,7 +109,8 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
                  const __grid_constant__ CUtensorMap tmap_v,
                  const __grid_constant__ CUtensorMap tmap_do,
                  const __grid_constant__ CUtensorMap tmap_dk,
-                 const __grid_constant__ CUtensorMap tmap_dv, const BwdParams p) {
+                 const __grid_constant__ CUtensorMap tmap_dv,
+                 const __grid_constant__ CUtensorMap tmap_dq, const BwdParams p) {
   using L = BwdSmem<kDP>;
   constexpr int kDBlocks = kDP / 64;
   constexpr int kKSteps = kDP / 16;     // contraction over the head dim (S, dP)
@@ -154,6 +156,7 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_dk);
     tma_prefetch_desc(&tmap_dv);
+    tma_prefetch_desc(&tmap_dq);
 #pragma unroll
     for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
@@ -290,25 +293,36 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
     }
 
-    // ---- drain dQ_i: my half of the head-dim columns, fp32 atomics into dq_acc
+    // ---- drain dQ_i: 32 head-dim columns at a time through a swizzled fp32 staging tile, then one
+    // TMA reduce-add per chunk: dq_acc[b,h, 128 rows, 32 cols] += staging (rows >= Nq are clipped).
+    // Thread (r, half) moves 16 of the 32 columns of row r.
     mbar_wait(bar_dq, ph, 64);
     tc_fence_after();
-    float* dq_row = p.dq_acc + (bh * p.Nq + row) * p.dq_ld + half * kHalfD;
-#pragma unroll
-    for (int cidx = 0; cidx < kHalfD / 32; ++cidx) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem + lane_base + kColdQ + half * kHalfD + cidx * 32, v);
+#pragma unroll 1
+    for (int cidx = 0; cidx < kDP / 32; ++cidx) {
+      uint8_t* stage = smem + L::kStage + (cidx & 1) * (kTileM * 128);
+      uint32_t v[16];
+      tmem_ld_x16(tmem + lane_base + kColdQ + cidx * 32 + half * 16, v);
+      if (tid == 0) tma_store_wait_read_1();  // the reduce that last read this staging tile is done
+      named_bar_sync(1, 256);
       tmem_wait_ld();
-      if (row_ok) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          red_add_v4(dq_row + cidx * 32 + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                     __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      for (int ch = 0; ch < 4; ++ch) {
+        const int chunk = half * 4 + ch;  // 16-byte chunk inside the 128-byte row
+        *reinterpret_cast<uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(v[ch * 4 + 0], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);
+      if (tid == 0) {
+        tma_reduce_add_3d(&tmap_dq, smem_u32(stage), cidx * 32, i * kTileM, static_cast<int>(bh));
+        tma_store_commit();
       }
     }
     tc_fence_before();
     __syncthreads();  // S / dQ columns and the P / dS tiles may be overwritten by the next tile
   }
+  if (tid == 0) tma_store_wait_read();  // staging tiles are re-used by nothing below, but be tidy
 
   // ---- epilogue: dV and scale * dK -> 16 bit -> swizzled smem (P / dS tiles) -> TMA store.
   // TMEM lane = key row here.  With no visible query tile (causal, keys beyond the last query)

@@ -330,8 +330,30 @@ int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse
 // backward launchers
 // ---------------------------------------------------------------------------------------------
 struct BwdMaps {
-  CUtensorMap q, k, v, d_o, dk, dv;
+  CUtensorMap q, k, v, d_o, dk, dv, dq;
 };
+
+// 3-D fp32 map over the contiguous dq accumulator [B*H, Nq, DP]: box {32 columns = one 128-byte
+// swizzle row, 128 rows, 1}; rows >= Nq of a partial tile are clipped by the reduce.
+int make_map_dq(CUtensorMap* map, float* base, int BH, int Nq, int DP) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(DP), static_cast<cuuint64_t>(Nq),
+                        static_cast<cuuint64_t>(BH)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(DP) * 4, static_cast<cuuint64_t>(Nq) * DP * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(dq accumulator) failed (CUresult %d) dims=[%d,%d,%d]",
+             static_cast<int>(r), DP, Nq, BH);
+    return fail(FA_ERR_CUDA, buf);
+  }
+  return FA_OK;
+}
 
 template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
@@ -342,7 +364,7 @@ int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int N
   int rc = set_smem(kernel, smem, &configured, device);
   if (rc) return rc;
   dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
-  kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, bp);
+  kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
@@ -667,6 +689,7 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   if ((rc = make_map(&m.d_o, d_o, B, H, Nq, D, dos, dtype, fa::kTileM))) return rc;
   if ((rc = make_map(&m.dk, dk, B, H, Nkv, D, dks, dtype, fa::kTileN))) return rc;
   if ((rc = make_map(&m.dv, dv, B, H, Nkv, D, dvs, dtype, fa::kTileN))) return rc;
+  if ((rc = make_map_dq(&m.dq, dq_accum, B * H, Nq, D))) return rc;
   fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale};
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 

@@ -236,12 +236,25 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
       ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 3-D tiled reduce-add smem -> global (the element type, fp32 here, comes from the tensor map):
+// global[box] += smem[box], performed by the L2 atomic units on whole 128-byte lines
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src_smem, int c0,
+                                                  int c1, int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 // wait until the smem source of all committed bulk stores has been read
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// wait until at most one committed bulk group still has its smem source unread
+__device__ __forceinline__ void tma_store_wait_read_1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
