@@ -194,6 +194,12 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr uint32_t idesc_q = make_idesc_f16(kTileM, kDP, kBF16, false, true);      // dQ
   const float c = p.scale_log2;
   const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+  // L_i / D_i of my query row, fetched one tile ahead so the global-load latency is not exposed
+  float lse_next = 0.f, dl_next = 0.f;
+  if (n_iter > 0 && i_begin * kTileM + r < p.Nq) {
+    lse_next = p.lse[bh * p.Nq + i_begin * kTileM + r];
+    dl_next = p.delta[bh * p.Nq + i_begin * kTileM + r];
+  }
 
 #pragma unroll 1
   for (int it = 0; it < n_iter; ++it) {
@@ -221,8 +227,13 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ---- P and dS for my half of the row
     const int row = i * kTileM + r;
     const bool row_ok = row < p.Nq;
-    const float lse = row_ok ? p.lse[bh * p.Nq + row] : 0.f;
-    const float dl = row_ok ? p.delta[bh * p.Nq + row] : 0.f;
+    const float lse = lse_next;
+    const float dl = dl_next;
+    if (it + 1 < n_iter) {
+      const int nrow = row + kTileM;
+      lse_next = (nrow < p.Nq) ? p.lse[bh * p.Nq + nrow] : 0.f;
+      dl_next = (nrow < p.Nq) ? p.delta[bh * p.Nq + nrow] : 0.f;
+    }
     const float nl = -lse;
     // masks are needed on the diagonal tile, on the last (partial) key tile and on partial Q tiles
     const bool need_mask = (kCausal && i == j) || (key0 + kTileN > p.Nkv) || ((i + 1) * kTileM > p.Nq);

@@ -22,6 +22,7 @@
 
 #include "../../include/fa_fwd_sm100.h"
 #include "fa_bwd_tc.cuh"
+#include "fa_bwd_ws.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
@@ -32,6 +33,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
+std::atomic<int> g_bwd_kernel{FA_BWD_KERNEL_TC1};  // measured faster than WS (tools/bench_bwd.py)
 #ifdef FA_TRACE
 unsigned long long* g_trace = nullptr;  // debug builds only (tools/trace_ws.py)
 #define FA_TP_TRACE , g_trace
@@ -358,13 +360,22 @@ int make_map_dq(CUtensorMap* map, float* base, int BH, int Nq, int DP) {
 template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
                   cudaStream_t stream) {
-  auto kernel = fa::fa_bwd_tc_kernel<kDP, kBF16, kCausal>;
-  constexpr int smem = fa::BwdSmem<kDP>::kTotal;
-  static std::atomic<uint64_t> configured{0};
-  int rc = set_smem(kernel, smem, &configured, device);
-  if (rc) return rc;
   dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
-  kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
+  if (g_bwd_kernel.load() == FA_BWD_KERNEL_TC1) {
+    auto kernel = fa::fa_bwd_tc_kernel<kDP, kBF16, kCausal>;
+    constexpr int smem = fa::BwdSmem<kDP>::kTotal;
+    static std::atomic<uint64_t> configured{0};
+    int rc = set_smem(kernel, smem, &configured, device);
+    if (rc) return rc;
+    kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
+  } else {
+    auto kernel = fa::fa_bwd_ws_kernel<kDP, kBF16, kCausal>;
+    constexpr int smem = fa::BwdWsSmem<kDP>::kTotal;
+    static std::atomic<uint64_t> configured{0};
+    int rc = set_smem(kernel, smem, &configured, device);
+    if (rc) return rc;
+    kernel<<<grid, fa::kBwdWsThreads, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
+  }
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
@@ -495,6 +506,11 @@ uint64_t fa_launch_count(void) { return g_launches.load(); }
 int fa_set_kernel(int kernel) {
   if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
+}
+
+int fa_set_bwd_kernel(int kernel) {
+  if (kernel != FA_BWD_KERNEL_TC1 && kernel != FA_BWD_KERNEL_WS) return -FA_ERR_INVALID_ARG;
+  return g_bwd_kernel.exchange(kernel);
 }
 
 int fa_select_kernel(int B, int H, int Nq, int Nkv, int D, const int64_t q_strides[4],

@@ -468,6 +468,10 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
 }
 #undef FA_R4
 
+__device__ __forceinline__ void st_shared_u16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // 16-bit packing
 // ---------------------------------------------------------------------------------------------

@@ -14,10 +14,11 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # FA_FWD_SM100_LIB selects another build of the same C-ABI (e.g. the FA_TRACE debug library)
 LIB_PATH = os.environ.get("FA_FWD_SM100_LIB") or os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
 
-FA_ABI_VERSION = 2
+FA_ABI_VERSION = 3
 FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
 FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0, 1, 2, 3, 4
 FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS = 0, 1, 2, 3, 4
+FA_BWD_KERNEL_TC1, FA_BWD_KERNEL_WS = 1, 2
 KERNEL_NAMES = {
     FA_KERNEL_AUTO: "auto",
     FA_KERNEL_SIMT: "simt",
@@ -36,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "fa_abi_version",
     "fa_select_kernel",
     "fa_set_kernel",
+    "fa_set_bwd_kernel",
     "fa_launch_count",
     "fa_umma_selftest",
 )
@@ -74,6 +76,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_select_kernel.restype = i
     lib.fa_set_kernel.argtypes = [i]
     lib.fa_set_kernel.restype = i
+    lib.fa_set_bwd_kernel.argtypes = [i]
+    lib.fa_set_bwd_kernel.restype = i
     lib.fa_launch_count.argtypes = []
     lib.fa_launch_count.restype = ctypes.c_uint64
     lib.fa_umma_selftest.argtypes = [vp, vp, vp, i, i, ctypes.c_uint32, ctypes.c_uint32, vp]
@@ -119,6 +123,13 @@ def set_kernel(kernel: int) -> int:
     prev = lib.fa_set_kernel(int(kernel))
     if prev < 0:
         raise ValueError(f"unknown kernel selector {kernel}")
+    return prev
+
+
+def set_bwd_kernel(kernel: int) -> int:
+    prev = lib.fa_set_bwd_kernel(int(kernel))
+    if prev < 0:
+        raise ValueError(f"unknown backward kernel selector {kernel}")
     return prev
 
 

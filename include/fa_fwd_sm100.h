@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FA_ABI_VERSION 2
+#define FA_ABI_VERSION 3
 
 /* element types (reference: host.cpp:32-44 dispatches on torch::kFloat16 / torch::kBFloat16) */
 #define FA_DTYPE_F16 0
@@ -121,6 +121,14 @@ const char* fa_last_error(void);
 
 /* FA_ABI_VERSION the library was built with. */
 int fa_abi_version(void);
+
+/* backward kernel selectors for fa_set_bwd_kernel() */
+#define FA_BWD_KERNEL_TC1 1    /* P and dS through shared memory (csrc/fa_bwd_tc.cuh); the default */
+#define FA_BWD_KERNEL_WS 2     /* warp-specialised, transposed scores, P^T / dS^T from TMEM (csrc/fa_bwd_ws.cuh) */
+
+/* Choose the backward kernel for subsequent fa_bwd_sm100() calls in this process (test /
+ * benchmarking hook).  Returns the previous setting or a negative error code. */
+int fa_set_bwd_kernel(int kernel);
 
 /*
  * Which kernel fa_fwd_sm100() would run for this problem (one of FA_KERNEL_*, never AUTO), or a

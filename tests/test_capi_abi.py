@@ -29,7 +29,7 @@ def test_header_symbols_all_exported():
 
 
 def test_abi_version_and_error_string():
-    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 2
+    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 3
     assert isinstance(_capi.last_error(), str)
 
 

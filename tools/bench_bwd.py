@@ -11,14 +11,18 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "flash-attention-v2-rdna3-minimal_b200"))
 import torch
+from rocwmma_fattn import _capi
 from rocwmma_fattn.FlashAttn import flash_attn_wmma
+
+_capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_WS if os.environ.get("FA_BWD", "tc1") == "ws"
+                     else _capi.FA_BWD_KERNEL_TC1)
 
 ns = [int(x) for x in sys.argv[1:]] or [1024, 4096, 16384]
 H, D = 16, 128
 torch.manual_seed(0)
 res = {}
 side = torch.cuda.Stream()
-for dt_name, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+for dt_name, dt in (("f16", torch.float16),) if os.environ.get("FA_BWD_QUICK") else (("f16", torch.float16), ("bf16", torch.bfloat16)):
     for causal in (False, True):
         for n in ns:
             q, k, v, d_o = (torch.rand(1, H, n, D, dtype=dt, device="cuda") for _ in range(4))
@@ -49,6 +53,6 @@ for dt_name, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
             res[f"{dt_name}_{'causal' if causal else 'full'}_n{n}"] = {
                 "ms": round(best, 4), "tflops": round(fl / best / 1e9, 1)}
             del keep, g
-print(json.dumps(res, indent=1))
+print(os.environ.get("FA_BWD", "tc1"), json.dumps({k: v["tflops"] for k, v in res.items()}))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_bwd.json"), "w"), indent=1)

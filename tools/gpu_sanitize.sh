@@ -1,0 +1,23 @@
+#!/bin/bash
+# compute-sanitizer over small forward + backward problems (memcheck, racecheck, synccheck)
+mkdir -p gpurun_out
+cat > /tmp/san.py <<'PY'
+import os, sys
+sys.path.insert(0, os.path.join(os.environ["GRAFT_REPO_ROOT"], "flash-attention-v2-rdna3-minimal_b200"))
+import torch
+from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
+torch.manual_seed(0)
+for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 512, 512, 128, torch.float16, False), (1, 1, 300, 200, 128, torch.bfloat16, True),
+                                      (1, 2, 128, 128, 64, torch.float16, False), (1, 1, 384, 384, 64, torch.bfloat16, True)]:
+    q = torch.rand(B, H, N, D, dtype=dt, device="cuda", requires_grad=True)
+    k = torch.rand(B, H, Nkv, D, dtype=dt, device="cuda", requires_grad=True)
+    v = torch.rand(B, H, Nkv, D, dtype=dt, device="cuda", requires_grad=True)
+    o = F.apply(q, k, v, None, causal)
+    o.backward(torch.rand_like(o))
+    torch.cuda.synchronize()
+    print("ok", B, H, N, Nkv, D, dt, causal, float(o.float().mean()), float(q.grad.float().abs().mean()))
+PY
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=fa_ python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitizer_$tool.log | head -8; grep -c "^ok" gpurun_out/sanitizer_$tool.log
+done
