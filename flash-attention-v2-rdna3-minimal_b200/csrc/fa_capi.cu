@@ -26,6 +26,7 @@
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
+#include "fa_fwd_sk.cuh"
 #include "umma_probe.cuh"
 
 namespace {
@@ -164,12 +165,15 @@ bool tma_ok_strides(const int64_t st[4]) {
   return true;
 }
 
+bool sk_eligible(const Problem& p, int n_sm);
+
 // pointer-independent part of the choice
 int choose_kernel_shape(const Problem& p) {
   const bool tc = (p.D % 8 == 0) && (p.D <= 128) && (p.scale > 0.f) && tma_ok_strides(p.qs) &&
                   tma_ok_strides(p.ks) && tma_ok_strides(p.vs) && tma_ok_strides(p.os);
   if (!tc) return FA_KERNEL_SIMT;
   if (p.Nq <= fa::kTileM) return FA_KERNEL_TC1;
+  if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   return FA_KERNEL_WS;
 }
 
@@ -254,11 +258,112 @@ int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
-  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f FA_TP_TRACE};
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
   kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent stream-K forward: per-(device, stream) workspace for the partial results of split units
+// ---------------------------------------------------------------------------------------------
+struct SkWorkspace {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  float* ws = nullptr;
+  int* flags = nullptr;
+  size_t ws_bytes = 0;
+  int flag_count = 0;
+};
+std::mutex g_sk_mu;
+std::vector<SkWorkspace> g_sk_ws;
+
+int sm_count(int device) {
+  static std::mutex mu;
+  static int cached[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 64 && cached[device] > 0) return cached[device];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  if (device < 64) cached[device] = n;
+  return n;
+}
+
+// Workspace for launches on `stream`, or nullptr if none can be provided right now (stream capture
+// in progress with nothing cached, allocation failure, too many streams): the caller then uses the
+// one-shot kernel.  Launches on one stream are ordered, so one slot set per stream is enough.
+SkWorkspace* get_sk_workspace(int device, cudaStream_t stream, size_t ws_bytes, int flag_count) {
+  std::lock_guard<std::mutex> lk(g_sk_mu);
+  for (auto& w : g_sk_ws)
+    if (w.device == device && w.stream == stream && w.ws_bytes >= ws_bytes && w.flag_count >= flag_count)
+      return &w;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  if (g_sk_ws.size() >= 16) return nullptr;
+  SkWorkspace w;
+  w.device = device;
+  w.stream = stream;
+  if (cudaMalloc(reinterpret_cast<void**>(&w.ws), ws_bytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&w.flags), flag_count * sizeof(int)) != cudaSuccess ||
+      cudaMemset(w.flags, 0, flag_count * sizeof(int)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (w.ws) cudaFree(w.ws);
+    if (w.flags) cudaFree(w.flags);
+    return nullptr;
+  }
+  w.ws_bytes = ws_bytes;
+  w.flag_count = flag_count;
+  g_sk_ws.reserve(16);  // pointers handed out stay valid
+  g_sk_ws.push_back(w);
+  return &g_sk_ws.back();
+}
+
+// shape-only eligibility (the SM count defaults to a B200's 148 when no device is consulted)
+bool sk_eligible(const Problem& p, int n_sm) {
+  if (p.causal || p.Nq % (2 * fa::kTileM) != 0 || n_sm <= 0) return false;
+  const long long units = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
+  // Correct for units >= n_sm (a CTA range then spans at least one whole unit); measured against the
+  // one-shot kernel on B200 (tools/ab_kernels.py, B=1 H=16 D=128): -1.5 % at 1.7 units per SM
+  // (N=4096), +12 % at 3.5 (N=8192), +3 % at 6.9 (N=16384) - so it is selected from 2 units per SM
+  return units >= 2LL * n_sm;
+}
+
+template <int kDP, bool kBF16>
+int launch_sk(const Plan& pl, float* lse, cudaStream_t stream, bool* launched) {
+  const Problem& p = pl.p;
+  *launched = false;
+  const int G = sm_count(pl.device);
+  const long long units = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
+  // an explicit FA_KERNEL_SK request runs from one unit per SM (tests exercise the split paths there)
+  const bool forced = g_forced_kernel.load() == FA_KERNEL_SK;
+  if (p.causal || p.Nq % (2 * fa::kTileM) != 0 || G <= 0 || units < (forced ? 1LL : 2LL) * G) return FA_OK;
+  const size_t ws_bytes = static_cast<size_t>(G + 1) * fa::SkSlot<kDP>::kFloats * sizeof(float);
+  SkWorkspace* w = get_sk_workspace(pl.device, stream, ws_bytes, 2 * (G + 1));
+  if (w == nullptr) return FA_OK;
+  auto kernel = fa::fa_fwd_sk_kernel<kDP, kBF16>;
+  constexpr int smem = fa::SkCfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  const int T = (p.Nkv + fa::kTileN - 1) / fa::kTileN;
+  const int P = p.Nq / (2 * fa::kTileM);
+  const long long U = static_cast<long long>(p.B) * p.H * P;
+  // all but the last full round are data-parallel; the last G + U % G units are split evenly
+  const int dp = (U % G == 0) ? static_cast<int>(U / G) : static_cast<int>(U / G) - 1;
+  const long long W = (U - static_cast<long long>(dp) * G) * T;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, w->ws, w->flags, W, dp, T, P FA_TP_TRACE};
+  kernel<<<G, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  *launched = true;
   return FA_OK;
 }
 
@@ -270,7 +375,7 @@ int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
-  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f FA_TP_TRACE};
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
   kernel<<<grid, 128, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
   FA_CUDA_TRY(cudaGetLastError());
@@ -281,6 +386,14 @@ int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
 template <int kDP, bool kBF16, bool kCausal>
 int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
   switch (kernel) {
+    case FA_KERNEL_SK: {
+      if constexpr (!kCausal) {
+        bool launched = false;
+        int rc = launch_sk<kDP, kBF16>(pl, lse, stream, &launched);
+        if (rc || launched) return rc;
+      }
+      return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // not eligible / no workspace
+    }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_TC1: return launch_tc1<kDP, kBF16, kCausal, false>(pl, lse, stream);
     case FA_KERNEL_TC1_PSMEM: return launch_tc1<kDP, kBF16, kCausal, true>(pl, lse, stream);
@@ -504,7 +617,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_SK) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 

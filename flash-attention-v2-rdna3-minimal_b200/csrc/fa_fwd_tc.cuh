@@ -19,6 +19,13 @@ struct TcParams {
   float* lse;            // [B,H,Nq] fp32, base-2 log-sum-exp of the scaled scores; may be null
   int Nq, Nkv, H;
   float scale_log2;      // scale * log2(e)
+  // persistent stream-K kernel only (fa_fwd_sk.cuh); zero / null otherwise
+  float* sk_ws;          // per-CTA partial results of split units
+  int* sk_flags;         // [gridDim.x][2] "partial of tile t is ready" flags, all zero between launches
+  long long sk_W;        // work items of the stream-K phase = (units - sk_dp * grid) * sk_T
+  int sk_dp;             // leading data-parallel rounds (one whole unit per CTA and round)
+  int sk_T;              // KV tiles per unit
+  int sk_P;              // 256-row query blocks per (batch, head)
 #ifdef FA_TRACE
   unsigned long long* trace;  // debug builds only: clock64() stamps of one CTA (tools/trace_ws.py)
 #endif

@@ -68,11 +68,143 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when th
 #define FA_EMU_PAIRS 1
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
-// The two softmax groups take turns in the max/exp section (experiment; off by default).
-#ifndef FA_SEQ
-#define FA_SEQ 0
-#endif
-constexpr bool kSeq = FA_SEQ != 0;
+
+// One softmax step of one thread: `s` holds its 64 raw scores of the current S tile (already loaded
+// from TMEM).  Masks them, exponentiates against the running max (first half speculatively against
+// the max of the previous tiles, see below), hands P to the MMA warp in two parts, rescales O when
+// the lazy-rescale rule fires and updates (m_run, l_run).  Shared by the one-shot and the
+// persistent kernel.
+//   tS / tO     TMEM addresses of my 64 S columns (P goes over the first 32) / my O columns
+//   col0        index of the first key of my half;  diag: this is the causal diagonal tile
+//   have_o      O_t already holds a partial sum (not the first KV tile of this pass)
+template <int kDP, bool kBF16>
+__device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
+                                                int r, int lane, int col0, int Nkv, bool diag,
+                                                float c, float& m_run, float& l_run, bool have_o,
+                                                float* my_max, const float* other_max, int pair_bar,
+                                                uint32_t bar_early, uint32_t bar_late) {
+  constexpr int kOHalf = kDP / 2;
+  const bool tail = (col0 + 64 > Nkv);
+  const bool masked = tail || diag;
+  int lim = 64;  // columns [0, lim) of my half are visible
+  if (masked) {
+    const int valid = tail ? (Nkv - col0) : 64;
+    lim = diag ? min(valid, r + 1 - half * 64) : valid;
+#pragma unroll
+    for (int i = 0; i < 64; ++i)
+      if (i >= lim) s[i] = -INFINITY;
+  }
+
+  // p = 2^(s*c - m*c) for one group of 4 columns: kEmuPairs of every 8 element pairs go through
+  // the FMA pipes (ex2_fma2), the rest through the MUFU
+  auto exp4 = [&](int i, float nmc_) {
+    ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc_, nmc_);
+    ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc_, nmc_);
+    if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
+      ex2_fma2(s[i], s[i + 1]);
+    } else {
+      s[i] = ex2_approx(s[i]);
+      s[i + 1] = ex2_approx(s[i + 1]);
+    }
+    if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
+      ex2_fma2(s[i + 2], s[i + 3]);
+    } else {
+      s[i + 2] = ex2_approx(s[i + 2]);
+      s[i + 3] = ex2_approx(s[i + 3]);
+    }
+  };
+
+  // Columns [0,32) are exponentiated against the running max of the PREVIOUS tiles while the
+  // max of this tile is still being reduced (the MUFU is the busiest pipe: the max, the pair
+  // exchange and the packing run in its shadow).  That is exact whenever the lazy-rescale rule
+  // keeps m_run anyway (max grew by < 2^8); otherwise the slow path below redoes the columns.
+  float nmc = -m_run * c;
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
+    mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
+    mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
+    mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
+    exp4(i, nmc);
+  }
+  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  *my_max = mx;
+  named_bar_sync(pair_bar, 64);
+  const float m_cand = fmaxf(fmaxf(mx, *other_max), m_run);
+  // both threads of the row see the same three numbers, so they take the same decision
+  const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
+  float alpha = 1.f;
+  if (__any_sync(0xffffffffu, grow)) {
+    // slow path (first tile; afterwards only when some row max grew by more than 2^8)
+    if (grow) {
+      alpha = ex2_approx((m_run - m_cand) * c);
+      m_run = m_cand;
+    }
+    if (have_o) {
+      // O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was issued before
+      // S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
+#pragma unroll 1
+      for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
+        uint32_t o[8];
+        tmem_ld_x8(tO + c8, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_x8(tO + c8, o);
+      }
+    }
+    // redo columns [0,32) against the new max: S is still intact in TMEM (no P stored yet)
+    nmc = -m_run * c;
+    tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
+    tmem_wait_ld();
+    if (masked) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i >= lim) s[i] = -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) exp4(i, nmc);
+  }
+
+  // ---- first half of my P columns -> TMEM -> "early" hand-off
+  {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(s[2 * i], s[2 * i + 1]);
+    tmem_st_x16(tS, pk);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_early);
+  }
+  // ---- second half, with the row sum of the first half in the MUFU shadow
+  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+  {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 32; i < 64; i += 4) {
+      exp4(i, nmc);
+      fadd2(sum0, sum1, sum0, sum1, s[i - 32], s[i - 31]);
+      fadd2(sum2, sum3, sum2, sum3, s[i - 30], s[i - 29]);
+      pk[(i - 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
+      pk[((i - 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
+    }
+    tmem_st_x16(tS + 16, pk);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bar_late);
+    }
+  }
+#pragma unroll
+  for (int i = 32; i < 64; i += 4) {
+    fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
+    fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
+  }
+  l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+}
 
 template <int kDP, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -106,7 +238,6 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_p_early = [&](int t) { return smem_u32(&bars[4 + t]); };
   auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
-  auto bar_seq = [&](int t) { return smem_u32(&bars[10 + t]); };        // kSeq only, 8 warps
   auto bar_kv_full = [&](int s) { return smem_u32(&bars[12 + s]); };    // tx, count 1
   auto bar_kv_empty = [&](int s) { return smem_u32(&bars[12 + kS + s]); };  // tcgen05.commit
 
@@ -143,7 +274,6 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_p_early(t), 8);
       mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
-      mbar_init(bar_seq(t), 8);
     }
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
@@ -323,141 +453,12 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
-      if (kSeq) {  // my turn?  tile 0 goes first; turn j of tile 1 follows turn j of tile 0
-        if (t == 0) {
-          if (j > 0 && j - 1 < n_t[1]) mbar_wait(bar_seq(0), (j - 1) & 1, 42);
-        } else {
-          if (j < n_t[0]) mbar_wait(bar_seq(1), j & 1, 43);
-        }
-      }
       FA_TR(tr_role, j, 2);
 
-      const int col0 = j * kTileN + half * 64;  // first key of my half
-      const bool tail = (col0 + 64 > p.Nkv);
-      const bool diag = kCausal && (j == diag_j);
-      const bool masked = tail || diag;
-      int lim = 64;  // columns [0, lim) of my half are visible
-      if (masked) {
-        const int valid = tail ? (p.Nkv - col0) : 64;
-        lim = diag ? min(valid, r + 1 - half * 64) : valid;
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= lim) s[i] = -INFINITY;
-      }
-
-      // p = 2^(s*c - m*c) for one group of 4 columns: kEmuPairs of every 8 element pairs go through
-      // the FMA pipes (ex2_fma2), the rest through the MUFU
-      auto exp4 = [&](int i, float nmc_) {
-        ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc_, nmc_);
-        ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc_, nmc_);
-        if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
-          ex2_fma2(s[i], s[i + 1]);
-        } else {
-          s[i] = ex2_approx(s[i]);
-          s[i + 1] = ex2_approx(s[i + 1]);
-        }
-        if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
-          ex2_fma2(s[i + 2], s[i + 3]);
-        } else {
-          s[i + 2] = ex2_approx(s[i + 2]);
-          s[i + 3] = ex2_approx(s[i + 3]);
-        }
-      };
-
-      // Columns [0,32) are exponentiated against the running max of the PREVIOUS tiles while the
-      // max of this tile is still being reduced (the MUFU is the busiest pipe: the max, the pair
-      // exchange and the packing run in its shadow).  That is exact whenever the lazy-rescale rule
-      // keeps m_run anyway (max grew by < 2^8); otherwise the slow path below redoes the columns.
-      float nmc = -m_run * c;
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
-        mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
-        mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
-        mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
-        exp4(i, nmc);
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      my_max[(j & 1) * 512] = mx;
-      named_bar_sync(pair_bar, 64);
-      const float m_cand = fmaxf(fmaxf(mx, other_max[(j & 1) * 512]), m_run);
-      // both threads of the row see the same three numbers, so they take the same decision
-      const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
-      float alpha = 1.f;
-      if (__any_sync(0xffffffffu, grow)) {
-        // slow path (first tile; afterwards only when some row max grew by more than 2^8)
-        if (grow) {
-          alpha = ex2_approx((m_run - m_cand) * c);
-          m_run = m_cand;
-        }
-        if (j > 0) {
-          // O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was issued before
-          // S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
-#pragma unroll 1
-          for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
-            uint32_t o[8];
-            tmem_ld_x8(tO + c8, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x8(tO + c8, o);
-          }
-        }
-        // redo columns [0,32) against the new max: S is still intact in TMEM (no P stored yet)
-        nmc = -m_run * c;
-        tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
-        tmem_wait_ld();
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= lim) s[i] = -INFINITY;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) exp4(i, nmc);
-      }
-      FA_TR(tr_role, j, 3);
-
-      // ---- first half of my P columns -> TMEM -> "early" hand-off
-      {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack2<kBF16>(s[2 * i], s[2 * i + 1]);
-        tmem_st_x16(tS, pk);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_early(t));
-        FA_TR(tr_role, j, 4);
-      }
-      // ---- second half, with the row sum of the first half in the MUFU shadow
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 32; i < 64; i += 4) {
-          exp4(i, nmc);
-          fadd2(sum0, sum1, sum0, sum1, s[i - 32], s[i - 31]);
-          fadd2(sum2, sum3, sum2, sum3, s[i - 30], s[i - 29]);
-          pk[(i - 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
-          pk[((i - 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
-        }
-        tmem_st_x16(tS + 16, pk);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_p_late(t));
-          if (kSeq) mbar_arrive(bar_seq(t ^ 1));
-        }
-        FA_TR(tr_role, j, 5);
-      }
-#pragma unroll
-      for (int i = 32; i < 64; i += 4) {
-        fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
-        fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
-      }
-      l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+      ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
+                                  kCausal && (j == diag_j), c, m_run, l_run, j > 0,
+                                  my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
+                                  bar_p_early(t), bar_p_late(t));
       FA_TR(tr_role, j, 6);
     }
 

@@ -14,10 +14,10 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # FA_FWD_SM100_LIB selects another build of the same C-ABI (e.g. the FA_TRACE debug library)
 LIB_PATH = os.environ.get("FA_FWD_SM100_LIB") or os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
 
-FA_ABI_VERSION = 3
+FA_ABI_VERSION = 4
 FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
 FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0, 1, 2, 3, 4
-FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS = 0, 1, 2, 3, 4
+FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS, FA_KERNEL_SK = 0, 1, 2, 3, 4, 5
 FA_BWD_KERNEL_TC1, FA_BWD_KERNEL_WS = 1, 2
 KERNEL_NAMES = {
     FA_KERNEL_AUTO: "auto",
@@ -25,6 +25,7 @@ KERNEL_NAMES = {
     FA_KERNEL_TC1: "tc1",
     FA_KERNEL_TC1_PSMEM: "tc1_psmem",
     FA_KERNEL_WS: "ws",
+    FA_KERNEL_SK: "sk",
 }
 
 # every symbol include/fa_fwd_sm100.h declares

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FA_ABI_VERSION 3
+#define FA_ABI_VERSION 4
 
 /* element types (reference: host.cpp:32-44 dispatches on torch::kFloat16 / torch::kBFloat16) */
 #define FA_DTYPE_F16 0
@@ -51,6 +51,9 @@ extern "C" {
 #define FA_KERNEL_TC1 2        /* tcgen05, one 128-row Q tile per CTA, P through TMEM */
 #define FA_KERNEL_TC1_PSMEM 3  /* as TC1 but P through shared memory */
 #define FA_KERNEL_WS 4         /* tcgen05, warp-specialised, two Q tiles per CTA (the fast path) */
+#define FA_KERNEL_SK 5         /* FA_KERNEL_WS made persistent: one CTA per SM, work split evenly over
+                                  (query block, KV tile) items; non-causal, Nq % 256 == 0, >= 1 query
+                                  block per SM; falls back to FA_KERNEL_WS otherwise */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu

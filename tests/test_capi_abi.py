@@ -29,7 +29,7 @@ def test_header_symbols_all_exported():
 
 
 def test_abi_version_and_error_string():
-    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 3
+    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 4
     assert isinstance(_capi.last_error(), str)
 
 
@@ -46,8 +46,9 @@ def _st(B, H, N, D):
 @pytest.mark.parametrize(
     "shape,expected",
     [
-        ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # BASELINE sweep point
-        ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),      # BASELINE config 5
+        ((1, 16, 8192, 8192, 128), _capi.FA_KERNEL_SK),       # BASELINE sweep point: 512 blocks >= 2 x 148 SMs
+        ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # 256 blocks < 2 per SM: one-shot kernel
+        ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_SK),      # BASELINE config 5
         ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
         ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad
         ((3, 7, 1537, 1234, 111), _capi.FA_KERNEL_SIMT),      # unpadded odd head dim
