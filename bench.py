@@ -164,7 +164,7 @@ def cpu_reference_run(steps: int, warmup: int, sample_n=(512, 1024, 2048)):
     }
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -184,7 +184,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -205,11 +205,22 @@ def make_pool(shape, dtype, device, min_bytes):
     return pool
 
 
+_CAPTURE_STREAM = None
+
+
+def capture_stream():
+    """One capture stream for every graph of the run (the library keeps per-stream workspaces)."""
+    global _CAPTURE_STREAM
+    if _CAPTURE_STREAM is None:
+        _CAPTURE_STREAM = torch.cuda.Stream()
+    return _CAPTURE_STREAM
+
+
 def time_variant(fa, pool, causal, iters, warm=3):
     """Average device time (ms) of one forward on rotating inputs (extra sweeps, not the headline):
     ``reps`` launches captured into a CUDA graph, replayed until ~``iters`` launches have run."""
     reps = max(2, min(len(pool), 16))
-    side = torch.cuda.Stream()
+    side = capture_stream()
 
     def fn():
         return [fa(*pool[i % len(pool)], None, causal) for i in range(reps)]
@@ -235,7 +246,21 @@ def time_variant(fa, pool, causal, iters, warm=3):
     return e0.elapsed_time(e1) / (n_rep * reps)
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the duration of the run and return a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str) -> None:
+        os.write(real, (text + "\n").encode())
+
+    return emit
+
+
 def main():
+    emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -247,7 +272,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -309,7 +334,7 @@ def main():
     # ctypes cost of one FlashAttentionFunction.apply, so an eager loop would time the host.  The K
     # steps (K x len(points) launches through the public entry point, rotating inputs) are captured
     # once into a CUDA graph and the timed region replays it: same kernels, same arguments.
-    side = torch.cuda.Stream(device=dev)
+    side = capture_stream()
 
     def capture(fn):
         g = torch.cuda.CUDAGraph()
@@ -430,11 +455,15 @@ def main():
     # ---- roofline of the dominant kernel (largest N of the step), per launch, one GPU's share
     dom_b, dom_n = points[-1]
     dom_ms = per_point_ms[-1]
+    _st = (H * dom_n * D, dom_n * D, D, 1)
+    dom_kernel = {_capi.FA_KERNEL_SK: "fa_fwd_sk_kernel", _capi.FA_KERNEL_WS: "fa_fwd_ws_kernel"}.get(
+        _capi.select_kernel(dom_b, H, dom_n, dom_n, D, _st, _st, _st, _st, _capi.FA_DTYPE_F16, False, D ** -0.5),
+        "fa_fwd kernel")
     dom_flops = flops(dom_b, H, dom_n, D)
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
-                "kernel": f"fa_fwd_ws_kernel<128,f16,non-causal> B={dom_b} H=16 N={dom_n}",
+                "kernel": f"{dom_kernel}<128,f16,non-causal> B={dom_b} H=16 N={dom_n}",
                 "flops_per_launch": dom_flops, "ms_per_launch": round(dom_ms, 5),
                 "peak_source": peaks["source"],
                 "frac_of_sustained": round(achieved / peaks["tflops_sustained"], 4) if peaks["tflops_sustained"] else None,
@@ -513,6 +542,22 @@ def main():
                 res[str(n)] = {"ms": round(ms, 5), "tflops": round(flops(1, H, n, D, causal) / (ms * 1e-3) / 1e12, 2)}
                 del pool
             extras[name] = res
+        # backward, secondary: dQ/dK/dV through flash_attn_wmma.backward,
+        # TFLOPS = 2.5 x forward FLOPs / t (bench_with_sdpa.py:39-40)
+        from rocwmma_fattn.FlashAttn import flash_attn_wmma
+
+        bwd = {}
+        for n in (4096, 16384):
+            q, k, v = pools[n][0]
+            d_o = torch.rand_like(q)
+            _, qp, kp, vp, o_pad, lse = flash_attn_wmma.forward(q, k, v, 64, 128, False, D ** -0.5, False)
+
+            def bfn(n=n, qp=qp, kp=kp, vp=vp, o_pad=o_pad, d_o=d_o, lse=lse):
+                return flash_attn_wmma.backward(qp, kp, vp, o_pad, d_o, lse, n, n, D, 128, 128, False, D ** -0.5, False)
+
+            ms = time_variant(lambda *a: bfn(), [(None, None, None)] * 2, False, iters=8)
+            bwd[str(n)] = {"ms": round(ms, 5), "tflops": round(2.5 * flops(1, H, n, D) / (ms * 1e-3) / 1e12, 2)}
+        extras["f16_backward_noncausal"] = bwd
         line["config"]["extra_sweeps"] = extras
         del pools
         torch.cuda.empty_cache()
@@ -524,7 +569,7 @@ def main():
                                 "host_cpus": cpu["host_cpus"]}
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
