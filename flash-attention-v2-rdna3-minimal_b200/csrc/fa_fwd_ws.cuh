@@ -68,6 +68,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when th
 #define FA_EMU_PAIRS 1
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
+// Turn-taking between the softmax groups of the two Q tiles (experiment): tile 1 starts its step on KV
+// tile j only after tile 0 has issued its last exponentials of step j, and tile 0 starts step j+1
+// only after tile 1's step j, so the two groups never compete for the MUFU.
+#ifndef FA_SEQ
+#define FA_SEQ 0
+#endif
+constexpr bool kSeq = FA_SEQ != 0;
 
 // One softmax step of one thread: `s` holds its 64 raw scores of the current S tile (already loaded
 // from TMEM).  Masks them, exponentiates against the running max (first half speculatively against
@@ -82,7 +89,8 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
                                                 float* my_max, const float* other_max, int pair_bar,
-                                                uint32_t bar_early, uint32_t bar_late) {
+                                                uint32_t bar_early, uint32_t bar_late,
+                                                uint32_t bar_turn = 0u) {
   constexpr int kOHalf = kDP / 2;
   const bool tail = (col0 + 64 > Nkv);
   const bool masked = tail || diag;
@@ -196,6 +204,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(bar_late);
+      if (bar_turn != 0u) mbar_arrive(bar_turn);  // FA_SEQ: the other tile's softmax may start
     }
   }
 #pragma unroll
@@ -238,6 +247,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_p_early = [&](int t) { return smem_u32(&bars[4 + t]); };
   auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
+  auto bar_turn = [&](int t) { return smem_u32(&bars[10 + t]); };       // kSeq: 8 warps of the other tile
   auto bar_kv_full = [&](int s) { return smem_u32(&bars[12 + s]); };    // tx, count 1
   auto bar_kv_empty = [&](int s) { return smem_u32(&bars[12 + kS + s]); };  // tcgen05.commit
 
@@ -274,6 +284,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_p_early(t), 8);
       mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
+      mbar_init(bar_turn(t), 8);
     }
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
@@ -453,12 +464,19 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
+      if (kSeq) {  // my turn?  tile 0 goes first; step j of tile 1 follows step j of tile 0
+        if (t == 0) {
+          if (j > 0 && j - 1 < n_t[1]) mbar_wait(bar_turn(0), (j - 1) & 1, 42);
+        } else {
+          if (j < n_t[0]) mbar_wait(bar_turn(1), j & 1, 43);
+        }
+      }
       FA_TR(tr_role, j, 2);
 
       ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
                                   kCausal && (j == diag_j), c, m_run, l_run, j > 0,
                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
-                                  bar_p_early(t), bar_p_late(t));
+                                  bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u);
       FA_TR(tr_role, j, 6);
     }
 

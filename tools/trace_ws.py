@@ -16,6 +16,7 @@ import torch
 from rocwmma_fattn import _capi
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction
 
+_capi.set_kernel(_capi.FA_KERNEL_WS)  # the timeline stamps live in the one-shot kernel
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 causal = len(sys.argv) > 2 and sys.argv[2] == "causal"
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2  # launches before the traced one (clock state)
