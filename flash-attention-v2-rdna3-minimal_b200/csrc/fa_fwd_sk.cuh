@@ -326,7 +326,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
 #pragma unroll 1
       for (int j = 0; j < n; ++j, ++g) {
-        mbar_wait(bar_s_full(t), g & 1, 40 + t);
+        mbar_wait_warp(bar_s_full(t), g & 1, 40 + t);
         tc_fence_after();
         float s[64];
         tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));

@@ -457,7 +457,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
       FA_TR(tr_role, j, 0);
-      mbar_wait(bar_s_full(t), j & 1, 40 + t);
+      mbar_wait_warp(bar_s_full(t), j & 1, 40 + t);
       tc_fence_after();
       FA_TR(tr_role, j, 1);
       float s[64];

@@ -203,6 +203,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// Whole-warp wait: lane 0 polls, the other lanes park at the warp barrier (32x fewer polls of the
+// barrier word; __syncwarp orders the lanes' later accesses after lane 0's acquire).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0) {
+#ifdef FA_WARP_WAIT
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, tag);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity, tag);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // proxies / fences
 // ---------------------------------------------------------------------------------------------
