@@ -330,10 +330,14 @@ SkWorkspace* get_sk_workspace(int device, cudaStream_t stream, size_t ws_bytes, 
 bool sk_eligible(const Problem& p, int n_sm) {
   if (p.causal || p.Nq % (2 * fa::kTileM) != 0 || n_sm <= 0) return false;
   const long long units = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
-  // Correct for units >= n_sm (a CTA range then spans at least one whole unit); measured against the
-  // one-shot kernel on B200 (tools/ab_kernels.py, B=1 H=16 D=128): -1.5 % at 1.7 units per SM
-  // (N=4096), +12 % at 3.5 (N=8192), +3 % at 6.9 (N=16384) - so it is selected from 2 units per SM
-  return units >= 2LL * n_sm;
+  // Correct from one unit per SM (a CTA range then spans at least one whole unit).  It pays where the
+  // one-shot kernel loses more than ~5 % to whole rounds: measured on B200 (tools/ab_bench.py, fp16
+  // B=1 H=16 D=128) 1371 vs 1298 TFLOPS at N=8192 (3.46 rounds -> 4: 15.6 % lost), 1434 vs 1437 at
+  // N=16384 (6.92 -> 7: 1.2 %), 1185 vs 1214 at N=4096 (1.73 -> 2, but too few KV tiles per CTA to
+  // amortise the two extra unit boundaries).
+  if (units < 2LL * n_sm) return false;
+  const long long rounds = (units + n_sm - 1) / n_sm;
+  return rounds * n_sm * 100 >= units * 105;
 }
 
 template <int kDP, bool kBF16>

@@ -33,18 +33,25 @@ struct SkSlot {
   static constexpr int kFloats = kOFloats + 2 * kTileM * 2;
 };
 
-// Shared memory: the Q tiles are double-buffered (the next unit's Q is loaded, and its first S tiles
-// are computed, under the current unit's last KV tiles and epilogue), paid for at D = 128 with a
-// K/V ring of 3 instead of 4 tiles and a single-buffered row-max exchange.  No alignment slack: the
-// dynamic shared-memory window starts 1024-byte aligned (checked at kernel start).
+// Shared memory: Q tiles (optionally double-buffered, see FA_SK_QDOUBLE), the K/V ring, barriers and
+// a single-buffered row-max exchange.  No alignment slack: the dynamic shared-memory window starts
+// 1024-byte aligned (checked at kernel start).
+// FA_SK_QDOUBLE=1 double-buffers the Q tiles (next unit's Q and first S under the current unit's
+// epilogue) at the price of a 3-deep instead of 4-deep K/V ring at D = 128.  Measured with the
+// three-part P hand-off: the deeper ring wins by 1-3 % at every sweep length, so the default is 0.
+#ifndef FA_SK_QDOUBLE
+#define FA_SK_QDOUBLE 0
+#endif
+constexpr bool kSkQDouble = FA_SK_QDOUBLE != 0;
+
 template <int kDP>
 struct SkCfg {
   static constexpr int kTileBytes = kTileM * kDP * 2;
-  static constexpr int kStages = (kDP == 128) ? 3 : 8;
+  static constexpr int kStages = (kDP == 128) ? (kSkQDouble ? 3 : 4) : 8;
   static constexpr int kQ = 0;                          // [2 buffers][2 tiles]; also O staging
-  static constexpr int kKV = kQ + 4 * kTileBytes;
+  static constexpr int kKV = kQ + (kSkQDouble ? 4 : 2) * kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 16 + 2 * kStages;
+  static constexpr int kNumBars = 18 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;  // float [2 tile][2 half][128]; also row sums
   static constexpr int kTotal = kMax + 2 * 2 * 128 * 4;
 };
@@ -82,6 +89,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // per tile, 8 softmax warps: "O_t has been read out of TMEM and the Q_t buffer (O staging) is
   // free again" - gates the Q load and the first PV of the next unit
   auto bar_tile_free = [&](int t) { return smem_u32(&bars[10 + t]); };
+  auto bar_p_mid = [&](int t) { return smem_u32(&bars[16 + 2 * kS + t]); };  // 8 softmax warps
   auto bar_kv_full = [&](int s) { return smem_u32(&bars[16 + s]); };    // tx, count 1
   auto bar_kv_empty = [&](int s) { return smem_u32(&bars[16 + kS + s]); };  // tcgen05.commit
 
@@ -130,6 +138,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
       mbar_init(bar_tile_free(t), 8);
+      mbar_init(bar_p_mid(t), 8);
     }
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
@@ -156,7 +165,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const float c = p.scale_log2;
 
   if (warp >= 16) {
-    setmaxnreg_dec<48>();  // 512 x 104 + 128 x 48 <= 640 x 96 (the walker state does not fit in 32)
+    setmaxnreg_dec<56>();  // 512 x 104 + 128 x 56 <= 640 x 96 (the walker state does not fit in 32)
     if (warp == 17) {
       // =======================================================================================
       // TMA producer
@@ -166,13 +175,14 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // Q tiles of segment `sgi` (its unit is `unit`) -> buffer sgi & 1.  The buffer was the O
         // staging of segment sgi - 2: wait until that store has read it.
         auto load_q = [&](int sgi, int unit) {
-          const int buf = sgi & 1;
+          const int buf = kSkQDouble ? (sgi & 1) : 0;
+          const int lag = kSkQDouble ? 2 : 1;  // the buffer was the O staging of segment sgi - lag
           const int row0 = (unit % p.sk_P) * 2 * kTileM;
           const int hh = (unit / p.sk_P) % p.H;
           const int bb = (unit / p.sk_P) / p.H;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (sgi >= 2) mbar_wait(bar_tile_free(t), (sgi - 2) & 1, 21);
+            if (sgi >= lag) mbar_wait(bar_tile_free(t), (sgi - lag) & 1, 21);
             mbar_arrive_expect_tx(bar_q_full(buf, t), C::kTileBytes);
 #pragma unroll
             for (int db = 0; db < kDBlocks; ++db)
@@ -180,7 +190,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                           db * 64, row0 + t * kTileM, hh, bb);
           }
         };
-        if (seg_more()) load_q(0, seg_unit());
+        if (kSkQDouble && seg_more()) load_q(0, seg_unit());
         for (int seg = 0; seg_more(); ++seg) {
           const int n = seg_n();
           const int t0 = seg_t0();
@@ -204,8 +214,9 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const int pre = min(2 * n, kS);
 #pragma unroll 1
           for (int x = 0; x < pre; ++x) load_kv(x);
+          if (!kSkQDouble) load_q(seg, unit);
           seg_next(n);
-          if (seg_more()) load_q(seg + 1, seg_unit());
+          if (kSkQDouble && seg_more()) load_q(seg + 1, seg_unit());
 #pragma unroll 1
           for (int x = pre; x < 2 * n; ++x) load_kv(x);
         }
@@ -247,24 +258,36 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           pv_step(t, v_lo, 1, 1);
           pv_step(t, v_lo, 4, 1);
           pv_step(t, v_lo, 5, 1);
-          mbar_wait(bar_p_late(t), g & 1, 35 + t);
-          tc_fence_after();
-          pv_step(t, v_lo, 2, 1);
-          pv_step(t, v_lo, 3, 1);
-          pv_step(t, v_lo, 6, 1);
-          pv_step(t, v_lo, 7, 1);
+          if (kPvParts == 3) {
+            mbar_wait(bar_p_mid(t), g & 1, 37 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 2, 1);
+            pv_step(t, v_lo, 6, 1);
+            mbar_wait(bar_p_late(t), g & 1, 35 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 3, 1);
+            pv_step(t, v_lo, 7, 1);
+          } else {
+            mbar_wait(bar_p_late(t), g & 1, 35 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 2, 1);
+            pv_step(t, v_lo, 3, 1);
+            pv_step(t, v_lo, 6, 1);
+            pv_step(t, v_lo, 7, 1);
+          }
           if (last) tc_commit(bar_o_final(t));
         };
 
         int g = 0;  // KV tiles processed so far by this CTA; ring indices are 2g (K) and 2g+1 (V)
         for (int seg = 0; seg_more(); ++seg) {
           const int n = seg_n();
+          const int qb = kSkQDouble ? (seg & 1) : 0;
           wait_kv(2 * g);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(bar_q_full(seg & 1, t), (seg >> 1) & 1, 33);
+            mbar_wait(bar_q_full(qb, t), kSkQDouble ? ((seg >> 1) & 1) : (seg & 1), 33);
             tc_fence_after();
-            issue_s(seg & 1, t, 2 * g);
+            issue_s(qb, t, 2 * g);
           }
           release_kv(2 * g);
 #pragma unroll 1
@@ -279,7 +302,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             issue_pv(0, 2 * g + 1, g, first, last);
             if (!last) {
               wait_kv(2 * g + 2);
-              issue_s(seg & 1, 0, 2 * g + 2);
+              issue_s(qb, 0, 2 * g + 2);
             }
             if (first && seg > 0) {
               mbar_wait(bar_tile_free(1), (seg - 1) & 1, 37);
@@ -288,7 +311,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             issue_pv(1, 2 * g + 1, g, first, last);
             release_kv(2 * g + 1);
             if (!last) {
-              issue_s(seg & 1, 1, 2 * g + 2);
+              issue_s(qb, 1, 2 * g + 2);
               release_kv(2 * g + 2);
             }
           }
@@ -334,7 +357,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_wait_ld();
         ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, (t0 + j) * kTileN + half * 64, p.Nkv,
                                     false, c, m_run, l_run, j > 0, my_max, other_max, pair_bar, bar_p_early(t),
-                                    bar_p_late(t));
+                                    bar_p_late(t), 0u, bar_p_mid(t));
       }
 
       // ---- end of the pass over this unit's KV range
@@ -400,7 +423,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           p.lse[static_cast<int64_t>(unit / p.sk_P) * p.Nq + row] = m_run * c + log2f(l_tot);
         const float inv_l = 1.f / l_tot;
         const float f_mine = scale_mine * inv_l, f_other = scale_other * inv_l;
-        uint8_t* stage = smem + C::kQ + ((seg & 1) * 2 + t) * C::kTileBytes;
+        const int qb = kSkQDouble ? (seg & 1) : 0;
+        uint8_t* stage = smem + C::kQ + (qb * 2 + t) * C::kTileBytes;
 #pragma unroll
         for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
           uint32_t o[32];
@@ -435,7 +459,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (tile_leader) {
 #pragma unroll
           for (int db = 0; db < kDBlocks; ++db)
-            tma_store_4d(&tmap_o, sQ + ((seg & 1) * 2 + t) * C::kTileBytes + db * 16384, db * 64, tile_row0,
+            tma_store_4d(&tmap_o, sQ + (qb * 2 + t) * C::kTileBytes + db * 16384, db * 64, tile_row0,
                          (unit / p.sk_P) % p.H, (unit / p.sk_P) / p.H);
           tma_store_commit();
           tma_store_wait_read();  // the Q_t buffer may be reloaded once the store has read it

@@ -44,7 +44,7 @@ struct WsCfg {
   static constexpr int kQ = 0;                           // 2 Q tiles (re-used as O staging)
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 12 + 2 * kStages;
+  static constexpr int kNumBars = 14 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;      // float [2 parity][2 tile][2 half][128]
   static constexpr int kFinal = kMax + 2 * 2 * 2 * 128 * 4;   // float [2 tile][2 half][128] row sums
   static constexpr int kTotal = kFinal + 2 * 2 * 128 * 4 + 1024;  // + alignment slack
@@ -75,6 +75,12 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 #define FA_SEQ 0
 #endif
 constexpr bool kSeq = FA_SEQ != 0;
+// P hand-off in 3 parts (32 + 16 + 16 keys per half; default) or 2 (32 + 32).  Measured: 3 parts are
+// +5.5 % at N=16384 and +7.7 % at N=4096 (the exposed tail of O += P V shrinks to two k-steps)
+#ifndef FA_PV_PARTS
+#define FA_PV_PARTS 3
+#endif
+constexpr int kPvParts = FA_PV_PARTS;
 
 // One softmax step of one thread: `s` holds its 64 raw scores of the current S tile (already loaded
 // from TMEM).  Masks them, exponentiates against the running max (first half speculatively against
@@ -90,7 +96,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
                                                 float c, float& m_run, float& l_run, bool have_o,
                                                 float* my_max, const float* other_max, int pair_bar,
                                                 uint32_t bar_early, uint32_t bar_late,
-                                                uint32_t bar_turn = 0u) {
+                                                uint32_t bar_turn = 0u, uint32_t bar_mid = 0u) {
   constexpr int kOHalf = kDP / 2;
   const bool tail = (col0 + 64 > Nkv);
   const bool masked = tail || diag;
@@ -197,8 +203,25 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
       fadd2(sum2, sum3, sum2, sum3, s[i - 30], s[i - 29]);
       pk[(i - 32) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
       pk[((i - 32) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
+      if (kPvParts == 3 && i == 44) {  // FA_PV_PARTS=3: columns [32,48) leave as a "mid" part
+        uint32_t lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) lo[e] = pk[e];
+        tmem_st_x8(tS + 16, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_mid);
+      }
     }
-    tmem_st_x16(tS + 16, pk);
+    if (kPvParts == 3) {
+      uint32_t hi[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hi[e] = pk[8 + e];
+      tmem_st_x8(tS + 24, hi);
+    } else {
+      tmem_st_x16(tS + 16, pk);
+    }
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
@@ -248,8 +271,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
   auto bar_turn = [&](int t) { return smem_u32(&bars[10 + t]); };       // kSeq: 8 warps of the other tile
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[12 + s]); };    // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[12 + kS + s]); };  // tcgen05.commit
+  auto bar_p_mid = [&](int t) { return smem_u32(&bars[12 + t]); };      // kPvParts == 3: 8 warps
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[14 + s]); };    // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[14 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -285,6 +309,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
       mbar_init(bar_turn(t), 8);
+      mbar_init(bar_p_mid(t), 8);
     }
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
@@ -388,12 +413,23 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           pv_step(t, v_lo, 1, 1);
           pv_step(t, v_lo, 4, 1);
           pv_step(t, v_lo, 5, 1);
-          mbar_wait(bar_p_late(t), j & 1, 35 + t);
-          tc_fence_after();
-          pv_step(t, v_lo, 2, 1);
-          pv_step(t, v_lo, 3, 1);
-          pv_step(t, v_lo, 6, 1);
-          pv_step(t, v_lo, 7, 1);
+          if (kPvParts == 3) {
+            mbar_wait(bar_p_mid(t), j & 1, 37 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 2, 1);
+            pv_step(t, v_lo, 6, 1);
+            mbar_wait(bar_p_late(t), j & 1, 35 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 3, 1);
+            pv_step(t, v_lo, 7, 1);
+          } else {
+            mbar_wait(bar_p_late(t), j & 1, 35 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 2, 1);
+            pv_step(t, v_lo, 3, 1);
+            pv_step(t, v_lo, 6, 1);
+            pv_step(t, v_lo, 7, 1);
+          }
           if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
         };
 
@@ -476,7 +512,8 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
                                   kCausal && (j == diag_j), c, m_run, l_run, j > 0,
                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
-                                  bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u);
+                                  bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
+                                  bar_p_mid(t));
       FA_TR(tr_role, j, 6);
     }
 
