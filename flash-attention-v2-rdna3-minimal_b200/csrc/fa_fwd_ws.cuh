@@ -31,8 +31,6 @@
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 / kernel_bf16.cu:329-576 and the
 // device GEMM helpers (:115-302); see fa_fwd_tc.cuh for the serial version of the same algorithm.
 #pragma once
-#include <type_traits>
-
 #include "fa_fwd_tc.cuh"
 
 namespace fa {
@@ -77,12 +75,6 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 #define FA_SEQ 0
 #endif
 constexpr bool kSeq = FA_SEQ != 0;
-// FA_MMA2=1: one MMA-issuing warp per Q tile (warps 16 and 18) instead of one for both, so a tile's
-// O += P V parts and next S are never queued behind the other tile's barrier waits.
-#ifndef FA_MMA2
-#define FA_MMA2 0
-#endif
-constexpr bool kMma2 = FA_MMA2 != 0;
 // P hand-off in 3 parts (32 + 16 + 16 keys per half; default) or 2 (32 + 32).  Measured: 3 parts are
 // +5.5 % at N=16384 and +7.7 % at N=4096 (the exposed tail of O += P V shrinks to two k-steps)
 #ifndef FA_PV_PARTS
@@ -322,7 +314,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
       mbar_init(bar_kv_full(s), 1);
-      mbar_init(bar_kv_empty(s), kMma2 ? 2 : 1);  // one tcgen05.commit per issuing warp
+      mbar_init(bar_kv_empty(s), 1);
     }
     fence_mbar_init();
   }
@@ -385,93 +377,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
       __syncwarp();
-    } else if (kMma2 && (warp == 16 || warp == 18)) {
-      // the tile index must be a compile-time constant: TMEM addresses derived from a runtime value
-      // make ptxas wrap every tcgen05.mma in an ELECT / R2UR loop (see the note at tmem_slot)
-      auto run_tile = [&](auto tile_c) {
-        constexpr int t = decltype(tile_c)::value;
-        constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
-        constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);
-        constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
-        auto wait_kv = [&](int idx) {
-          mbar_wait(bar_kv_full(idx % kS), (idx / kS) & 1, 30);
-          tc_fence_after();
-        };
-        // both warps release every slot (an empty commit arrives at once), so the ring barrier
-        // always collects two arrivals even where only one tile still has KV tiles left (causal)
-        auto release_kv = [&](int idx) { tc_commit(bar_kv_empty(idx % kS)); };
-        auto issue_s = [&](int j) {
-          const uint32_t k_lo = smem_desc_lo(sKV + ((2 * j) % kS) * C::kTileBytes, 16);
-          const uint32_t q_lo = smem_desc_lo(sQ + t * C::kTileBytes, 16);
-#pragma unroll
-          for (int k = 0; k < kKSteps; ++k) {
-            const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
-            umma_ss2(tmem + col_s(t), q_lo + off, desc_hi, k_lo + off, desc_hi, idesc_s, k > 0);
-          }
-          tc_commit(bar_s_full(t));
-        };
-        auto pv_step = [&](uint32_t v_lo, int ks, uint32_t acc) {
-          umma_ts2(tmem + col_o(t), tmem + col_s(t) + (ks >> 2) * 64 + (ks & 3) * 8,
-                   v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
-        };
-        auto issue_pv = [&](int j) {
-          const uint32_t v_lo = smem_desc_lo(sKV + ((2 * j + 1) % kS) * C::kTileBytes, 16384);
-          mbar_wait(bar_p_early(t), j & 1, 31 + t);
-          tc_fence_after();
-          pv_step(v_lo, 0, j > 0);
-          pv_step(v_lo, 1, 1);
-          pv_step(v_lo, 4, 1);
-          pv_step(v_lo, 5, 1);
-          if (kPvParts == 3) {
-            mbar_wait(bar_p_mid(t), j & 1, 37 + t);
-            tc_fence_after();
-            pv_step(v_lo, 2, 1);
-            pv_step(v_lo, 6, 1);
-            mbar_wait(bar_p_late(t), j & 1, 35 + t);
-            tc_fence_after();
-            pv_step(v_lo, 3, 1);
-            pv_step(v_lo, 7, 1);
-          } else {
-            mbar_wait(bar_p_late(t), j & 1, 35 + t);
-            tc_fence_after();
-            pv_step(v_lo, 2, 1);
-            pv_step(v_lo, 3, 1);
-            pv_step(v_lo, 6, 1);
-            pv_step(v_lo, 7, 1);
-          }
-          if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
-        };
-        if (n_max > 0) {
-          wait_kv(0);
-          if (n_t[t] > 0) {
-            mbar_wait(bar_q_full(t), 0, 33);
-            tc_fence_after();
-            issue_s(0);
-          }
-          release_kv(0);
-        }
-#pragma unroll 1
-        for (int j = 0; j < n_max; ++j) {
-          const int nx = j + 1;
-          wait_kv(2 * j + 1);
-          if (j < n_t[t]) issue_pv(j);
-          release_kv(2 * j + 1);
-          if (nx < n_max) {
-            wait_kv(2 * nx);
-            if (nx < n_t[t]) issue_s(nx);
-            release_kv(2 * nx);
-          }
-        }
-      };
-      if (elect_one()) {
-        if (warp == 16) {
-          run_tile(std::integral_constant<int, 0>{});
-        } else {
-          run_tile(std::integral_constant<int, 1>{});
-        }
-      }
-      __syncwarp();
-    } else if (!kMma2 && warp == 16) {
+    } else if (warp == 16) {
       if (elect_one()) {
         constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
         constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);
