@@ -79,3 +79,32 @@ def test_backward_entry_has_the_reference_signature_and_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         FlashAttn.flash_attn_wmma.backward(t, t, t, t, t, torch.zeros(1, 1, 8), 8, 8, 8, 128, 128, False,
                                            0.35, False)
+
+
+def test_sdpa_front_end_is_strict_and_installable():
+    """rocwmma_fattn.sdpa: torch-SDPA-shaped adapter; unsupported calls raise unless
+    the caller passes a fallback explicitly; install() / uninstall() swap torch's function."""
+    from rocwmma_fattn import sdpa
+
+    q = torch.zeros(1, 2, 8, 16, dtype=torch.float16)
+    with pytest.raises(NotImplementedError, match="CUDA"):
+        sdpa.scaled_dot_product_attention(q, q, q)
+    assert "attn_mask" in sdpa.supported(q, q, q, attn_mask=torch.ones(8, 8, dtype=torch.bool))
+    assert "dropout" in sdpa.supported(q, q, q, dropout_p=0.1)
+    calls = []
+
+    def fb(query, key, value, **kw):
+        calls.append(kw)
+        return query
+
+    assert sdpa.scaled_dot_product_attention(q, q, q, is_causal=True, fallback=fb) is q
+    assert calls and calls[0]["is_causal"] is True
+    stock = torch.nn.functional.scaled_dot_product_attention
+    sdpa.install()
+    try:
+        assert torch.nn.functional.scaled_dot_product_attention is not stock
+        with pytest.raises(NotImplementedError):
+            torch.nn.functional.scaled_dot_product_attention(q, q, q)
+    finally:
+        sdpa.uninstall()
+    assert torch.nn.functional.scaled_dot_product_attention is stock
