@@ -13,8 +13,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -194,7 +196,7 @@ struct PlanCache {
   std::mutex mu;
   std::vector<Plan> plans;
   uint64_t clock = 0;
-  static constexpr size_t kCap = 64;
+  static constexpr size_t kCap = 256;
 
   static bool same(const Plan& a, const void* q, const void* k, const void* v, const void* o,
                    const Problem& p, int device) {
@@ -707,14 +709,40 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
     w.cap_lse = bytes_lse;
   }
 
-  // Chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D].
-  // Aim for >= 8 chunks of >= 4 MiB of input each so copies and kernels overlap.
-  size_t per_head = q_head + 2 * kv_head;
-  size_t hg = (size_t(4) << 20) / per_head;
-  if (hg < 1) hg = 1;
-  if (hg > (heads + 7) / 8) hg = (heads + 7) / 8;
-  if (hg < 1) hg = 1;
-  const size_t n_chunks = (heads + hg - 1) / hg;
+  // Chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D].  The
+  // H2D stream is busy from the first byte to the last, so the call takes
+  //   T(n) = H2D_total + n * c_issue + (compute_total + D2H_total) / n
+  // (the tail of the last chunk is all that is not hidden; c_issue = the ~10 runtime calls a chunk
+  // costs on the host, ~40 us measured on B200 boxes: tools/e2e_probe.py).  n = sqrt(tail / c_issue)
+  // minimises it: 1 chunk at N=512 (was 8: 0.72 ms -> see profiles/r01_e2e_probe.txt), 8 at N=16384.
+  std::vector<size_t> chunk_heads;
+  {
+    const double flops = 4.0 * double(heads) * Nq * Nkv * D * (causal ? 0.5 : 1.0);
+    const double tail_us = flops / 1.0e9 + double(bytes_q) / 50.0e3 + 12.0;
+    double n = std::sqrt(tail_us / 40.0);
+    const char* e = std::getenv("FA_HOST_CHUNKS");
+    if (e != nullptr && std::atof(e) > 0) n = std::atof(e);  // "0": planner count, no tail split
+    size_t nc = n < 1.0 ? 1 : static_cast<size_t>(n + 0.5);
+    if (nc > heads) nc = heads;
+    const size_t hg = (heads + nc - 1) / nc;
+    for (size_t h0 = 0; h0 < heads; h0 += hg) chunk_heads.push_back(h0 + hg <= heads ? hg : heads - h0);
+    // Halve the last chunk while that shortens the exposed tail (its kernel + its D2H) by more than
+    // the ~25 us of copy start-up and event hand-offs an extra chunk costs on the device.  A CTA's
+    // run time is set by Nkv alone (~1.6 us per 128-key tile), so the kernel term stops shrinking
+    // once the chunk no longer fills the SMs.
+    auto tail = [&](size_t nh) {
+      const double cta_us = 10.0 + 1.6 * double((Nkv + 127) / 128) * (causal ? 0.5 : 1.0);
+      const double waves = std::ceil(double(nh) * double((Nq + 255) / 256) / 148.0);
+      return cta_us * waves + double(nh * q_head) / 50.0e3;
+    };
+    while (e == nullptr && chunk_heads.back() >= 2 &&
+           tail(chunk_heads.back()) - tail(chunk_heads.back() / 2) > 25.0) {
+      const size_t last = chunk_heads.back();
+      chunk_heads.back() = last - last / 2;
+      chunk_heads.push_back(last / 2);
+    }
+  }
+  const size_t n_chunks = chunk_heads.size();
   while (w.ev_in.size() < n_chunks) {
     cudaEvent_t e1, e2;
     FA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
@@ -723,13 +751,22 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
     w.ev_run.push_back(e2);
   }
 
+  // FA_HOST_TIMING=1: print host enqueue time, device span and total per call (diagnostic)
+  static const bool timing = std::getenv("FA_HOST_TIMING") != nullptr;
+  static cudaEvent_t t_ev[2] = {nullptr, nullptr};
+  static std::vector<cudaEvent_t> t_chunk;
+  const auto t_cpu0 = std::chrono::steady_clock::now();
+  if (timing) {
+    if (t_ev[0] == nullptr) { cudaEventCreate(&t_ev[0]); cudaEventCreate(&t_ev[1]); }
+    cudaEventRecord(t_ev[0], w.s_in);
+  }
   const char* hq = static_cast<const char*>(q);
   const char* hk = static_cast<const char*>(k);
   const char* hv = static_cast<const char*>(v);
   char* ho = static_cast<char*>(o);
-  for (size_t c = 0; c < n_chunks; ++c) {
-    const size_t h0 = c * hg;
-    const size_t nh = (h0 + hg <= heads) ? hg : heads - h0;
+  size_t h0 = 0;
+  for (size_t c = 0; c < n_chunks; h0 += chunk_heads[c], ++c) {
+    const size_t nh = chunk_heads[c];
     char* dq = static_cast<char*>(w.dq) + h0 * q_head;
     char* dk = static_cast<char*>(w.dk) + h0 * kv_head;
     char* dv = static_cast<char*>(w.dv) + h0 * kv_head;
@@ -739,6 +776,11 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
     FA_CUDA_TRY(cudaMemcpyAsync(dv, hv + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
     FA_CUDA_TRY(cudaEventRecord(w.ev_in[c], w.s_in));
     FA_CUDA_TRY(cudaStreamWaitEvent(w.s_run, w.ev_in[c], 0));
+    if (timing) {
+      while (t_chunk.size() < 4 * (c + 1)) { cudaEvent_t e; cudaEventCreate(&e); t_chunk.push_back(e); }
+      cudaEventRecord(t_chunk[4 * c + 0], w.s_in);
+      cudaEventRecord(t_chunk[4 * c + 1], w.s_run);
+    }
     // the chunk is a [1, nh, N, D] problem
     Problem p{};
     p.B = 1; p.H = static_cast<int>(nh); p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype;
@@ -749,13 +791,31 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
     float* dl = (lse != nullptr) ? w.dlse + h0 * Nq : nullptr;
     if ((rc = run_device(dq, dk, dv, dout, dl, p, w.s_run))) return rc;
     FA_CUDA_TRY(cudaEventRecord(w.ev_run[c], w.s_run));
+    if (timing) cudaEventRecord(t_chunk[4 * c + 2], w.s_run);
     FA_CUDA_TRY(cudaStreamWaitEvent(w.s_out, w.ev_run[c], 0));
     FA_CUDA_TRY(cudaMemcpyAsync(ho + h0 * q_head, dout, nh * q_head, cudaMemcpyDeviceToHost, w.s_out));
     if (lse != nullptr)
       FA_CUDA_TRY(cudaMemcpyAsync(lse + h0 * Nq, dl, nh * Nq * sizeof(float),
                                   cudaMemcpyDeviceToHost, w.s_out));
+    if (timing) cudaEventRecord(t_chunk[4 * c + 3], w.s_out);
   }
+  const auto t_cpu1 = std::chrono::steady_clock::now();
+  if (timing) cudaEventRecord(t_ev[1], w.s_out);
   FA_CUDA_TRY(cudaStreamSynchronize(w.s_out));
+  if (timing) {
+    const auto t_cpu2 = std::chrono::steady_clock::now();
+    float dev_ms = 0.f;
+    cudaEventElapsedTime(&dev_ms, t_ev[0], t_ev[1]);
+    fprintf(stderr, "[fa_fwd_sm100_host] N=%d chunks=%zu enqueue %.3f ms, device span %.3f ms, total %.3f ms\n",
+            Nq, n_chunks, std::chrono::duration<double, std::milli>(t_cpu1 - t_cpu0).count(), dev_ms,
+            std::chrono::duration<double, std::milli>(t_cpu2 - t_cpu0).count());
+    for (size_t c = 0; c < n_chunks; ++c) {
+      float t[4];
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], t_ev[0], t_chunk[4 * c + i]);
+      fprintf(stderr, "    chunk %zu: H2D done %.3f, kernel start %.3f, kernel done %.3f, D2H done %.3f\n", c,
+              t[0], t[1], t[2], t[3]);
+    }
+  }
   return FA_OK;
 }
 
