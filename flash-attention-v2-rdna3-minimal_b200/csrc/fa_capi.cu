@@ -29,6 +29,7 @@
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
 #include "fa_fwd_sk.cuh"
+#include "fa_fwd_wide.cuh"
 #include "umma_probe.cuh"
 
 namespace {
@@ -171,9 +172,10 @@ bool sk_eligible(const Problem& p, int n_sm);
 
 // pointer-independent part of the choice
 int choose_kernel_shape(const Problem& p) {
-  const bool tc = (p.D % 8 == 0) && (p.D <= 128) && (p.scale > 0.f) && tma_ok_strides(p.qs) &&
+  const bool tc = (p.D % 8 == 0) && (p.D <= 256) && (p.scale > 0.f) && tma_ok_strides(p.qs) &&
                   tma_ok_strides(p.ks) && tma_ok_strides(p.vs) && tma_ok_strides(p.os);
   if (!tc) return FA_KERNEL_SIMT;
+  if (p.D > 128) return FA_KERNEL_WIDE;  // two Q tiles no longer fit in TMEM: one tile, two S buffers
   if (p.Nq <= fa::kTileM) return FA_KERNEL_TC1;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   return FA_KERNEL_WS;
@@ -390,6 +392,22 @@ int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
 }
 
 template <int kDP, bool kBF16, bool kCausal>
+int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_wide_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::WideCfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
+  dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
+  kernel<<<grid, fa::kWideThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+template <int kDP, bool kBF16, bool kCausal>
 int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
   switch (kernel) {
     case FA_KERNEL_SK: {
@@ -420,6 +438,24 @@ int launch_tc(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
     if (ca) return launch_tc_variant<DP, false, true>(kernel, pl, lse, stream);      \
     return launch_tc_variant<DP, false, false>(kernel, pl, lse, stream);             \
   } while (0)
+  if (p.D > 128) {
+    if (kernel != FA_KERNEL_WIDE)
+      return fail(FA_ERR_UNSUPPORTED, "head dims 129..256 are served by FA_KERNEL_WIDE (or FA_KERNEL_SIMT) only");
+#define FA_DISPATCH_WIDE(DP)                                                  \
+  do {                                                                        \
+    if (bf) {                                                                 \
+      if (ca) return launch_wide<DP, true, true>(pl, lse, stream);            \
+      return launch_wide<DP, true, false>(pl, lse, stream);                   \
+    }                                                                         \
+    if (ca) return launch_wide<DP, false, true>(pl, lse, stream);             \
+    return launch_wide<DP, false, false>(pl, lse, stream);                    \
+  } while (0)
+    if (p.D <= 192) FA_DISPATCH_WIDE(192);
+    FA_DISPATCH_WIDE(256);
+#undef FA_DISPATCH_WIDE
+  }
+  if (kernel == FA_KERNEL_WIDE)
+    return fail(FA_ERR_UNSUPPORTED, "FA_KERNEL_WIDE serves head dims 129..256 only");
   if (p.D <= 64) FA_DISPATCH(64);
   FA_DISPATCH(128);
 #undef FA_DISPATCH
@@ -553,7 +589,7 @@ int resolve_kernel(const Problem& p, const void* q, const void* k, const void* v
   if (forced != FA_KERNEL_AUTO) {
     if (forced != FA_KERNEL_SIMT && kernel == FA_KERNEL_SIMT)
       return fail(FA_ERR_UNSUPPORTED,
-                  "forced tensor-core kernel cannot serve this problem (needs D % 8 == 0, D <= 128, "
+                  "forced tensor-core kernel cannot serve this problem (needs D % 8 == 0, D <= 256, "
                   "scale > 0, 16-byte aligned pointers and strides)");
     kernel = forced;
   }
@@ -623,7 +659,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_SK) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WIDE) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 

@@ -90,13 +90,15 @@ constexpr int kPvParts = FA_PV_PARTS;
 //   tS / tO     TMEM addresses of my 64 S columns (P goes over the first 32) / my O columns
 //   col0        index of the first key of my half;  diag: this is the causal diagonal tile
 //   have_o      O_t already holds a partial sum (not the first KV tile of this pass)
+//   bar_o       0, or the mbarrier (with parity o_parity) that tells PV(j-1) has left the tensor cores
 template <int kDP, bool kBF16>
 __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
                                                 float* my_max, const float* other_max, int pair_bar,
                                                 uint32_t bar_early, uint32_t bar_late,
-                                                uint32_t bar_turn = 0u, uint32_t bar_mid = 0u) {
+                                                uint32_t bar_turn = 0u, uint32_t bar_mid = 0u,
+                                                uint32_t bar_o = 0u, uint32_t o_parity = 0u) {
   constexpr int kOHalf = kDP / 2;
   const bool tail = (col0 + 64 > Nkv);
   const bool masked = tail || diag;
@@ -157,7 +159,12 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     }
     if (have_o) {
       // O_t *= alpha on my half of the row.  PV_t(j-1) has completed - it was issued before
-      // S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.
+      // S_t(j), whose commit we waited for - and PV_t(j) waits for bar_p_early.  (The wide kernel
+      // issues S(j) ahead of PV(j-1) and passes the barrier PV(j-1) commits to instead.)
+      if (bar_o != 0u) {
+        mbar_wait(bar_o, o_parity, 44);
+        tc_fence_after();
+      }
 #pragma unroll 1
       for (int c8 = 0; c8 < kOHalf; c8 += 8) {  // 8 columns at a time: keeps s[] in registers
         uint32_t o[8];

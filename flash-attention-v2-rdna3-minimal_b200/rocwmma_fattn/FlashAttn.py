@@ -32,7 +32,8 @@ __all__ = [
 ]
 
 _TMA_D_ALIGN = 8  # head dim multiple of 16 bytes for the tensor-core (TMA) kernels
-_TC_MAX_D = 128
+_TC_MAX_D = 256      # forward: ws / sk / tc1 kernels up to 128, the wide kernel up to 256
+_TC_MAX_D_BWD = 128  # backward kernels
 
 
 def _dtype_code(dt: torch.dtype) -> int:
@@ -91,7 +92,7 @@ def _forward(q, k, v, causal, scale, bnhd, want_lse):
     causal = bool(causal)
 
     # head dims that are not a multiple of 8 cannot be addressed by TMA: zero-pad them (zeros change
-    # neither q.k nor the first D columns of p.v); D > 128 goes to the generic kernel unpadded.
+    # neither q.k nor the first D columns of p.v); D > 256 goes to the generic kernel unpadded.
     d_pad = (-D) % _TMA_D_ALIGN if D < _TC_MAX_D else 0
     qp, kp, vp = _prepare(q, d_pad), _prepare(k, d_pad), _prepare(v, d_pad)
     o_full = torch.empty_like(qp)
@@ -119,9 +120,9 @@ def _backward(qp, kp, vp, o_full, d_o, lse, D, causal, scale, bnhd):
     if not qp.is_cuda:
         raise RuntimeError("rocwmma_fattn (B200 build) runs on CUDA tensors only; there is no CPU fallback")
     DP = qp.shape[3]
-    if DP > _TC_MAX_D or DP % _TMA_D_ALIGN:
+    if DP > _TC_MAX_D_BWD or DP % _TMA_D_ALIGN:
         raise NotImplementedError(
-            f"the sm_100a backward kernel covers head dims up to {_TC_MAX_D} (got {D}); larger head "
+            f"the sm_100a backward kernel covers head dims up to {_TC_MAX_D_BWD} (got {D}); larger head "
             "dims run forward-only in this build")
     if d_o.dtype != qp.dtype:
         d_o = d_o.to(qp.dtype)  # host.cpp:49-57 dispatches on dO's dtype; ours follows q's

@@ -53,7 +53,9 @@ def _st(B, H, N, D):
         ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
         ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad
         ((3, 7, 1537, 1234, 111), _capi.FA_KERNEL_SIMT),      # unpadded odd head dim
-        ((1, 2, 300, 300, 256), _capi.FA_KERNEL_SIMT),        # head dim > 128
+        ((1, 2, 300, 300, 256), _capi.FA_KERNEL_WIDE),        # head dim 129..256: one Q tile, two S buffers
+        ((1, 16, 4096, 4096, 160), _capi.FA_KERNEL_WIDE),     # bench_with_sdpa.py:259-261 sweep point D = 16 * 10
+        ((1, 2, 300, 300, 264), _capi.FA_KERNEL_SIMT),        # head dim > 256
         ((2, 4, 77, 300, 40), _capi.FA_KERNEL_TC1),
     ],
 )
