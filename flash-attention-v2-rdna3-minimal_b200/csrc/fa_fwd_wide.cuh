@@ -186,6 +186,10 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
           umma_ts2(tmem + kColO, tmem + buf * 128 + (ks >> 2) * 64 + (ks & 3) * 8,
                    v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
         };
+        // Observe PV(j-1)'s phase of bar_o before arming the next one: keeps the barrier at most one
+        // phase ahead of its (rare) softmax waiters.  Free in the tensor-bound regime: S(j+1) is still
+        // queued behind PV(j-1) when this returns.
+        if (j > 0) mbar_wait(bar_o, (j - 1) & 1, 35);
         mbar_wait(bar_p_early(buf), par, 31);
         tc_fence_after();
         pv_step(0, j > 0);

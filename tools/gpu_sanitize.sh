@@ -17,6 +17,21 @@ for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 512, 512, 128, torch.float16, False
     torch.cuda.synchronize()
     print("ok", B, H, N, Nkv, D, dt, causal, float(o.float().mean()), float(q.grad.float().abs().mean()))
 PY
+cat > /tmp/san_wide.py <<'PY'
+import os, sys
+sys.path.insert(0, os.path.join(os.environ["GRAFT_REPO_ROOT"], "flash-attention-v2-rdna3-minimal_b200"))
+import torch
+from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
+torch.manual_seed(0)
+# head dims 129..256: forward only (fa_fwd_wide_kernel), several KV tiles so the ring and both S buffers wrap
+for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 640, 640, 256, torch.float16, False), (1, 1, 300, 700, 160, torch.bfloat16, True),
+                                      (1, 1, 512, 512, 192, torch.float16, True)]:
+    q, k, v = (torch.randn(B, H, n, D, dtype=dt, device="cuda") for n in (N, Nkv, Nkv))
+    o = F.apply(q, k, v, None, causal)
+    torch.cuda.synchronize()
+    print("ok", B, H, N, Nkv, D, dt, causal, float(o.float().mean()))
+PY
+if [ -n "$SAN_ONLY_WIDE" ]; then cp /tmp/san_wide.py /tmp/san.py; else cat /tmp/san_wide.py >> /tmp/san.py; fi
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=fa_ python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "== $tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitizer_$tool.log | head -8; grep -c "^ok" gpurun_out/sanitizer_$tool.log
