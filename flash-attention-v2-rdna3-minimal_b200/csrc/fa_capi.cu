@@ -178,6 +178,11 @@ int choose_kernel_shape(const Problem& p) {
   if (p.D > 128) return FA_KERNEL_WIDE;  // two Q tiles no longer fit in TMEM: one tile, two S buffers
   if (p.Nq <= fa::kTileM) return FA_KERNEL_TC1;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
+  // Causal with fewer than two 256-row blocks per SM: the one-tile arrangement halves the scheduling
+  // grain, which matters more than its extra K/V traffic while the triangle leaves SMs idle (measured
+  // fp16 H=16 N=4096 causal: 763 vs 726 TFLOPS at D=128, 412 vs 360 at D=64; at N=16384 ws wins).
+  if (p.causal && static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) < 2 * 148)
+    return FA_KERNEL_WIDE;
   return FA_KERNEL_WS;
 }
 
@@ -452,13 +457,15 @@ int launch_tc(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
   } while (0)
     if (p.D <= 192) FA_DISPATCH_WIDE(192);
     FA_DISPATCH_WIDE(256);
-#undef FA_DISPATCH_WIDE
   }
-  if (kernel == FA_KERNEL_WIDE)
-    return fail(FA_ERR_UNSUPPORTED, "FA_KERNEL_WIDE serves head dims 129..256 only");
+  if (kernel == FA_KERNEL_WIDE) {  // forced: the one-tile arrangement at head dims <= 128 (experiments)
+    if (p.D <= 64) FA_DISPATCH_WIDE(64);
+    FA_DISPATCH_WIDE(128);
+  }
   if (p.D <= 64) FA_DISPATCH(64);
   FA_DISPATCH(128);
 #undef FA_DISPATCH
+#undef FA_DISPATCH_WIDE
 }
 
 int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse, const Problem& p,

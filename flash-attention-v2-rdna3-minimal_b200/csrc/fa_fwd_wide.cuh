@@ -31,9 +31,10 @@ constexpr int kWideThreads = 320;
 
 template <int kDP>
 struct WideCfg {
-  static_assert(kDP == 192 || kDP == 256, "wide kernel: padded head dim 192 or 256");
+  static_assert(kDP == 64 || kDP == 128 || kDP == 192 || kDP == 256, "wide kernel: padded head dim");
   static constexpr int kTileBytes = kTileM * kDP * 2;
-  static constexpr int kStages = (kDP == 256) ? 2 : 3;  // K/V ring slots (one K or one V tile each)
+  // K/V ring slots (one K or one V tile each): what fits next to the Q tile
+  static constexpr int kStages = (kDP == 256) ? 2 : (kDP == 192) ? 3 : (kDP == 128) ? 5 : 8;
   static constexpr int kQ = 0;                           // Q tile (re-used as O staging)
   static constexpr int kKV = kQ + kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;

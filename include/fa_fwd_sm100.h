@@ -54,7 +54,8 @@ extern "C" {
 #define FA_KERNEL_SK 5         /* FA_KERNEL_WS made persistent: one CTA per SM, work split evenly over
                                   (query block, KV tile) items; non-causal, Nq % 256 == 0, >= 1 query
                                   block per SM; falls back to FA_KERNEL_WS otherwise */
-#define FA_KERNEL_WIDE 6       /* tcgen05, head dims 129..256: one Q tile per CTA, double-buffered S */
+#define FA_KERNEL_WIDE 6       /* tcgen05, one Q tile per CTA with the score tile double-buffered: head dims
+                                  129..256, and small causal problems at head dims <= 128 */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu

@@ -66,10 +66,24 @@ def test_kernel_selection_is_pure_host_logic(shape, expected):
     assert k == expected
 
 
+@pytest.mark.parametrize(
+    "n,expected",
+    [
+        (4096, _capi.FA_KERNEL_WIDE),   # BASELINE config 4 point: 256 blocks < 2 per SM -> 128-row scheduling grain
+        (8192, _capi.FA_KERNEL_WS),     # 512 blocks: the two-tile kernel's shared K/V traffic wins again
+        (16384, _capi.FA_KERNEL_WS),
+        (128, _capi.FA_KERNEL_TC1),
+    ],
+)
+def test_kernel_selection_causal(n, expected):
+    st = _st(1, 16, n, 128)
+    assert _capi.select_kernel(1, 16, n, n, 128, st, st, st, st, _capi.FA_DTYPE_F16, True, 128 ** -0.5) == expected
+
+
 def test_kernel_selection_bnhd_strides_and_bad_strides():
     B, H, N, D = 2, 8, 512, 128
     bnhd = (N * H * D, D, H * D, 1)  # logical (b,h,n,d) strides of a [B,N,H,D] tensor
-    assert _capi.select_kernel(B, H, N, N, D, bnhd, bnhd, bnhd, bnhd, _capi.FA_DTYPE_BF16, True,
+    assert _capi.select_kernel(B, H, N, N, D, bnhd, bnhd, bnhd, bnhd, _capi.FA_DTYPE_BF16, False,
                                0.1) == _capi.FA_KERNEL_WS
     odd = (H * N * (D + 4), N * (D + 4), D + 4, 1)  # row stride not a multiple of 16 bytes
     assert _capi.select_kernel(B, H, N, N, D, odd, odd, odd, odd, _capi.FA_DTYPE_F16, False,

@@ -1,5 +1,6 @@
 """Forward throughput at head dims > 128 (fa_fwd_wide.cuh) next to torch SDPA on the same tensors.
-Not a bench.py metric: a development table for DESIGN.md.  python tools/bench_wide.py"""
+Not a bench.py metric: a development table for DESIGN.md.  python tools/bench_wide.py
+(BENCH_D=40,64,80 BENCH_N=1024,4096 selects other head dims / lengths)"""
 import os
 import sys
 
@@ -24,12 +25,19 @@ def timed(fn, iters):
     return a.elapsed_time(b) / iters
 
 
+DS = tuple(int(x) for x in os.environ.get("BENCH_D", "160,192,256").split(","))
+NS = tuple(int(x) for x in os.environ.get("BENCH_N", "2048,4096,8192,16384").split(","))
+
+
 def main():
     H = 16
+    forced = os.environ.get("BENCH_KERNEL")
+    if forced:
+        _capi.set_kernel({v: k for k, v in _capi.KERNEL_NAMES.items()}[forced])
     for dtype in (torch.float16, torch.bfloat16):
         for causal in (False, True):
-            for D in (160, 192, 256):
-                for N in (2048, 4096, 8192, 16384):
+            for D in DS:
+                for N in NS:
                     q, k, v = (torch.rand((1, H, N, D), dtype=dtype, device="cuda") for _ in range(3))
                     fl = 4.0 * H * N * N * D * (0.5 if causal else 1.0)
                     iters = max(5, min(50, int(3e12 / fl)))

@@ -20,8 +20,9 @@ _capi.set_kernel(_capi.FA_KERNEL_WS)  # the timeline stamps live in the one-shot
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 causal = len(sys.argv) > 2 and sys.argv[2] == "causal"
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2  # launches before the traced one (clock state)
+D = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 torch.manual_seed(0)
-q, k, v = (torch.rand(1, 16, N, 128, dtype=torch.float16, device="cuda") for _ in range(3))
+q, k, v = (torch.rand(1, 16, N, D, dtype=torch.float16, device="cuda") for _ in range(3))
 buf = torch.zeros(5 * 128 * 8, dtype=torch.int64, device="cuda")
 for _ in range(warm):
     FlashAttentionFunction.apply(q, k, v, None, causal)
@@ -75,5 +76,5 @@ stats["cta_ns"] = g1 - g0
 stats["sm_mhz_in_kernel"] = round((c1 - c0) / max(1, g1 - g0) * 1e3, 1)
 print(json.dumps(stats, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", f"trace_ws_n{N}{'_causal' if causal else ''}.json"), "w") as fh:
+with open(os.path.join(ROOT, "gpurun_out", f"trace_ws_n{N}_d{D}{'_causal' if causal else ''}.json"), "w") as fh:
     json.dump({"stats": stats, "raw": t.tolist()}, fh)
