@@ -183,6 +183,10 @@ int choose_kernel_shape(const Problem& p) {
   // fp16 H=16 N=4096 causal: 763 vs 726 TFLOPS at D=128, 412 vs 360 at D=64; at N=16384 ws wins).
   if (p.causal && static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) < 2 * 148)
     return FA_KERNEL_WIDE;
+  // Any mask, when every 128-row tile gets its own SM in one round: twice the CTAs of the two-tile kernel
+  // and a shorter iteration (graph-timed, fp16 H=16 D=128: N=512 252 vs 179 TFLOPS, N=1024 654 vs 460;
+  // at N=2048 - 256 tiles, two rounds - the two-tile kernel is back in front, 1081 vs 875).
+  if (static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM) <= 148) return FA_KERNEL_WIDE;
   return FA_KERNEL_WS;
 }
 

@@ -36,6 +36,14 @@ _TC_MAX_D = 256      # forward: ws / sk / tc1 kernels up to 128, the wide kernel
 _TC_MAX_D_BWD = 128  # backward kernels
 
 
+def _raw_stream(dev_index: int) -> int:
+    """cudaStream_t of torch's current stream on that device (the launch stream)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev_index)
+    except AttributeError:  # private API moved: the public spelling is just slower
+        return torch.cuda.current_stream(dev_index).cuda_stream
+
+
 def _dtype_code(dt: torch.dtype) -> int:
     if dt == torch.float16:
         return _capi.FA_DTYPE_F16
@@ -98,17 +106,24 @@ def _forward(q, k, v, causal, scale, bnhd, want_lse):
     o_full = torch.empty_like(qp)
     lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device) if want_lse else None
 
-    with torch.cuda.device(q.device):
-        stream = torch.cuda.current_stream(q.device).cuda_stream
-        rc = _capi.lib.fa_fwd_sm100(
-            qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), o_full.data_ptr(),
-            lse.data_ptr() if lse is not None else None,
-            B, H, Nq, Nkv, D + d_pad,
-            _capi.strides4(_logical_strides(qp, bnhd)), _capi.strides4(_logical_strides(kp, bnhd)),
-            _capi.strides4(_logical_strides(vp, bnhd)), _capi.strides4(_logical_strides(o_full, bnhd)),
-            _dtype_code(qp.dtype), int(causal), float(scale), stream,
-        )
-    _capi.check(rc, "fa_fwd_sm100")
+    dev_index = q.device.index
+    args = (
+        qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), o_full.data_ptr(),
+        lse.data_ptr() if lse is not None else None,
+        B, H, Nq, Nkv, D + d_pad,
+        _capi.strides4(_logical_strides(qp, bnhd)), _capi.strides4(_logical_strides(kp, bnhd)),
+        _capi.strides4(_logical_strides(vp, bnhd)), _capi.strides4(_logical_strides(o_full, bnhd)),
+        _dtype_code(qp.dtype), int(causal), float(scale),
+    )
+    # the call costs a few microseconds of Python on top of the launch; at N <= 1024 that is as long as
+    # the kernel, so skip the device guard when q already lives on the current device
+    if torch.cuda.current_device() == dev_index:
+        rc = _capi.lib.fa_fwd_sm100(*args, _raw_stream(dev_index))
+    else:
+        with torch.cuda.device(dev_index):
+            rc = _capi.lib.fa_fwd_sm100(*args, _raw_stream(dev_index))
+    if rc:
+        _capi.check(rc, "fa_fwd_sm100")
     o = o_full[..., :D] if d_pad else o_full
     return o, lse, (qp, kp, vp, o_full), (causal, float(scale), Nq, Nkv, D, bnhd)
 

@@ -110,8 +110,19 @@ def check(code: int, where: str) -> None:
         raise FlashAttnError(code, where)
 
 
+_STRIDES_CACHE: dict = {}
+
+
 def strides4(st) -> "ctypes.Array":
-    return _I64x4(int(st[0]), int(st[1]), int(st[2]), int(st[3]))
+    """int64[4] for the C-ABI.  The arrays are read-only on the C side, so one per distinct stride
+    tuple is kept (a forward call passes four of them; building each costs ~1 us)."""
+    key = tuple(st)
+    arr = _STRIDES_CACHE.get(key)
+    if arr is None:
+        if len(_STRIDES_CACHE) > 4096:
+            _STRIDES_CACHE.clear()
+        arr = _STRIDES_CACHE[key] = _I64x4(int(st[0]), int(st[1]), int(st[2]), int(st[3]))
+    return arr
 
 
 def last_error() -> str:

@@ -52,6 +52,9 @@ def _st(B, H, N, D):
         ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),      # BASELINE config 5: 110.7 rounds, one-shot
         ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
         ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad
+        ((1, 16, 1024, 1024, 128), _capi.FA_KERNEL_WIDE),     # sweep point: 128 tiles <= 148 SMs, one round of one-tile CTAs
+        ((1, 16, 512, 512, 128), _capi.FA_KERNEL_WIDE),
+        ((1, 16, 2048, 2048, 128), _capi.FA_KERNEL_WS),       # 256 tiles: two rounds -> two-tile kernel
         ((3, 7, 1537, 1234, 111), _capi.FA_KERNEL_SIMT),      # unpadded odd head dim
         ((1, 2, 300, 300, 256), _capi.FA_KERNEL_WIDE),        # head dim 129..256: one Q tile, two S buffers
         ((1, 16, 4096, 4096, 160), _capi.FA_KERNEL_WIDE),     # bench_with_sdpa.py:259-261 sweep point D = 16 * 10
@@ -83,8 +86,9 @@ def test_kernel_selection_causal(n, expected):
 def test_kernel_selection_bnhd_strides_and_bad_strides():
     B, H, N, D = 2, 8, 512, 128
     bnhd = (N * H * D, D, H * D, 1)  # logical (b,h,n,d) strides of a [B,N,H,D] tensor
+    # a tensor-core kernel serves BNHD views in place (64 tiles <= 148 SMs: the one-tile arrangement)
     assert _capi.select_kernel(B, H, N, N, D, bnhd, bnhd, bnhd, bnhd, _capi.FA_DTYPE_BF16, False,
-                               0.1) == _capi.FA_KERNEL_WS
+                               0.1) == _capi.FA_KERNEL_WIDE
     odd = (H * N * (D + 4), N * (D + 4), D + 4, 1)  # row stride not a multiple of 16 bytes
     assert _capi.select_kernel(B, H, N, N, D, odd, odd, odd, odd, _capi.FA_DTYPE_F16, False,
                                0.1) == _capi.FA_KERNEL_SIMT

@@ -16,6 +16,22 @@ def timed(fn, iters):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if os.environ.get("BENCH_GRAPH"):  # launch-bound sizes: time a CUDA graph of 20 calls instead
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            keep = [fn() for _ in range(20)]
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(max(1, iters // 4)):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        del keep
+        return a.elapsed_time(b) / (20 * max(1, iters // 4))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
