@@ -23,6 +23,8 @@ __device__ __forceinline__ void ffma1(float& a, float c, float d) { asm volatile
 __device__ __forceinline__ void fmax3(float& a, float b, float c) { asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a) : "f"(b), "f"(c)); }
 __device__ __forceinline__ void fmax2(float& a, float b) { asm volatile("max.f32 %0, %0, %1;" : "+f"(a) : "f"(b)); }
 __device__ __forceinline__ void f2fp(uint32_t& d, float a, float b) { asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); }
+__device__ __forceinline__ void ex2h2(uint32_t& a) { asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(a)); }
+__device__ __forceinline__ void ex2b2(uint32_t& a) { asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(a)); }
 __device__ __forceinline__ void imadshl(int& a, int b) { asm volatile("mad.lo.s32 %0, %1, 8388608, %0;" : "+r"(a) : "r"(b)); }
 
 // kind: 0 MUFU  1 FFMA2  2 FFMA  3 FADD2  4 FMNMX3  5 FMNMX  6 F2FP  7 IMAD
@@ -33,6 +35,9 @@ __global__ void bench(long long* out, float seed) {
   float x[8];
   uint32_t u[4] = {0, 0, 0, 0};
   int n[4] = {1, 2, 3, 4};
+  uint32_t h2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h2[i] = 0xb800b400u + i * 0x00010001u + threadIdx.x;  // small negative halves
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = seed + i * 0.001f + threadIdx.x * 1e-6f;
   long long t0 = clock64();
@@ -78,6 +83,12 @@ __global__ void bench(long long* out, float seed) {
       } else if (KIND == 12) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) { x[i * 2] = ex2(x[i * 2]); ffma2(x[4 + i * 2], x[5 + i * 2], 0.999f, 0.001f); x[i * 2 + 1] = ex2(x[i * 2 + 1]); f2fp(u[i], x[i * 2], x[i * 2 + 1]); }
+      } else if (KIND == 14) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ex2h2(h2[i]);
+      } else if (KIND == 15) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ex2b2(h2[i]);
       } else if (KIND == 13) {
         // 8 "instructions slots" = 4 elements' worth twice is awkward; do one group of 4 elements:
         // 2 FFMA2 + 4 MUFU + 2 F2FP + 2 FADD2 + 1 FMNMX3 = 11 instrs (counted as 8 for the report /8*11)
@@ -94,6 +105,8 @@ __global__ void bench(long long* out, float seed) {
   float acc = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc += x[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += h2[i];
   acc += u[0] + u[1] + u[2] + u[3] + n[0] + n[1] + n[2] + n[3];
   if (acc == 12345.678f) out[1023] = 1;
   if ((threadIdx.x & 31) == 0) out[blockIdx.x * 32 + (threadIdx.x >> 5)] = t1 - t0;
@@ -137,6 +150,8 @@ int main() {
   run<11>("FFMA2+F2FP 1:1", d_out, 8);
   run<12>("MUFU+FFMA2+F2FP 2:1:1", d_out, 8);
   run<13>("softmax mix (11 instr)", d_out, 11);
+  run<14>("ex2.f16x2 (2 results/instr)", d_out, 8);
+  run<15>("ex2.bf16x2 (2 results/instr)", d_out, 8);
   cudaError_t e = cudaGetLastError();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
