@@ -31,6 +31,7 @@
 #include "fa_fwd_sk.cuh"
 #include "fa_fwd_wide.cuh"
 #include "umma_probe.cuh"
+#include "umma2_probe.cuh"
 
 namespace {
 
@@ -979,6 +980,31 @@ int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mo
     if ((rc = set_smem(fa::umma_probe_kernel<false>, smem))) return rc;
     fa::umma_probe_kernel<false><<<1, 128, smem, s>>>(ma, mb, static_cast<const uint16_t*>(a), out,
                                                       mode, lbo, sbo);
+  }
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+int fa_umma2_selftest(const void* a, const void* b, float* out, int dtype, int mode, void* stream) {
+  if (a == nullptr || b == nullptr || out == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "a, b and out must not be null");
+  if (mode < 0 || mode > 1) return fail(FA_ERR_INVALID_ARG, "mode must be 0 or 1");
+  if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
+    return fail(FA_ERR_INVALID_ARG, "dtype must be FA_DTYPE_F16 or FA_DTYPE_BF16");
+  int dev;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  const int smem = 65536 + 128 + 1024;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == FA_DTYPE_BF16) {
+    if ((rc = set_smem(fa::umma2_probe_kernel<true>, smem))) return rc;
+    fa::umma2_probe_kernel<true><<<2, 128, smem, s>>>(static_cast<const uint16_t*>(a),
+                                                      static_cast<const uint16_t*>(b), out, mode);
+  } else {
+    if ((rc = set_smem(fa::umma2_probe_kernel<false>, smem))) return rc;
+    fa::umma2_probe_kernel<false><<<2, 128, smem, s>>>(static_cast<const uint16_t*>(a),
+                                                       static_cast<const uint16_t*>(b), out, mode);
   }
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);

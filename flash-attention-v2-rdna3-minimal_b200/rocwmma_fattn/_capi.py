@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = (
     "fa_set_bwd_kernel",
     "fa_launch_count",
     "fa_umma_selftest",
+    "fa_umma2_selftest",
 )
 
 _I64x4 = ctypes.c_int64 * 4
@@ -85,6 +86,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_launch_count.restype = ctypes.c_uint64
     lib.fa_umma_selftest.argtypes = [vp, vp, vp, i, i, ctypes.c_uint32, ctypes.c_uint32, vp]
     lib.fa_umma_selftest.restype = i
+    lib.fa_umma2_selftest.argtypes = [vp, vp, vp, i, i, vp]
+    lib.fa_umma2_selftest.restype = i
     if lib.fa_abi_version() != FA_ABI_VERSION:
         raise RuntimeError(
             f"{LIB_PATH}: ABI version {lib.fa_abi_version()} != expected {FA_ABI_VERSION}; rebuild"

@@ -161,6 +161,14 @@ uint64_t fa_launch_count(void);
 int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mode, uint32_t lbo,
                      uint32_t sbo, void* stream);
 
+/*
+ * CTA-pair (cluster of 2, tcgen05 cta_group::2) plumbing probe: out[256,128] (fp32) = A[256,128] * B with
+ * every operand 16-bit, each CTA of the pair holding its own 128 rows of A / out and half of B.
+ *   mode 0  A from shared memory (K-major); b = B as [n=128][k=128] row-major, CTA r takes rows 64r..64r+63
+ *   mode 1  A from tensor memory;           b = B as [k=128][n=128] row-major, CTA r takes columns 64r..64r+63
+ */
+int fa_umma2_selftest(const void* a, const void* b, float* out, int dtype, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
