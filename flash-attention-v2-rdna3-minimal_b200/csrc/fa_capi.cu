@@ -30,6 +30,7 @@
 #include "fa_fwd_ws.cuh"
 #include "fa_fwd_sk.cuh"
 #include "fa_fwd_wide.cuh"
+#include "fa_fwd_wide2.cuh"
 #include "umma_probe.cuh"
 #include "umma2_probe.cuh"
 
@@ -38,6 +39,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
+std::atomic<int> g_wide_pairs{1};  // head dims 193..256, non-causal: CTA-pair kernel (fa_set_wide_pairs)
 std::atomic<int> g_bwd_kernel{FA_BWD_KERNEL_TC1};  // measured faster than WS (tools/bench_bwd.py)
 #ifdef FA_TRACE
 unsigned long long* g_trace = nullptr;  // debug builds only (tools/trace_ws.py)
@@ -201,6 +203,7 @@ struct Plan {
   Problem p;
   int device;
   CUtensorMap mq, mk, mv, mo;
+  CUtensorMap mk64;  // K with a 64-key box (CTA-pair kernel: each CTA loads half of a K tile); D > 192 only
   uint64_t stamp;
 };
 
@@ -237,6 +240,7 @@ struct PlanCache {
     if ((rc = make_map(&pl.mk, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.mv, v, p.B, p.H, p.Nkv, p.D, p.vs, p.dtype, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.mo, o, p.B, p.H, p.Nq, p.D, p.os, p.dtype, fa::kTileM))) return rc;
+    if (p.D > 192 && (rc = make_map(&pl.mk64, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN / 2))) return rc;
     if (plans.size() < kCap) {
       plans.push_back(pl);
     } else {
@@ -417,6 +421,24 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   return FA_OK;
 }
 
+// CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 256, non-causal
+template <bool kBF16>
+int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_wide2_kernel<kBF16>;
+  constexpr int smem = fa::Wide2Cfg::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
+  const int tiles = (p.Nq + fa::kTileM - 1) / fa::kTileM;
+  dim3 grid((tiles + 1) & ~1, p.H, p.B);  // whole pairs: an odd last tile gets a partner that is all padding
+  kernel<<<grid, fa::kWideThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 template <int kDP, bool kBF16, bool kCausal>
 int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
   switch (kernel) {
@@ -461,6 +483,8 @@ int launch_tc(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
     return launch_wide<DP, false, false>(pl, lse, stream);                    \
   } while (0)
     if (p.D <= 192) FA_DISPATCH_WIDE(192);
+    if (!ca && g_wide_pairs.load(std::memory_order_relaxed))
+      return bf ? launch_wide2<true>(pl, lse, stream) : launch_wide2<false>(pl, lse, stream);
     FA_DISPATCH_WIDE(256);
   }
   if (kernel == FA_KERNEL_WIDE) {  // forced: the one-tile arrangement at head dims <= 128 (experiments)
@@ -674,6 +698,8 @@ int fa_set_kernel(int kernel) {
   if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WIDE) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
+
+int fa_set_wide_pairs(int enable) { return g_wide_pairs.exchange(enable ? 1 : 0); }
 
 int fa_set_bwd_kernel(int kernel) {
   if (kernel != FA_BWD_KERNEL_TC1 && kernel != FA_BWD_KERNEL_WS) return -FA_ERR_INVALID_ARG;

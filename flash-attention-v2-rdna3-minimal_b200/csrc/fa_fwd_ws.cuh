@@ -91,7 +91,8 @@ constexpr int kPvParts = FA_PV_PARTS;
 //   col0        index of the first key of my half;  diag: this is the causal diagonal tile
 //   have_o      O_t already holds a partial sum (not the first KV tile of this pass)
 //   bar_o       0, or the mbarrier (with parity o_parity) that tells PV(j-1) has left the tensor cores
-template <int kDP, bool kBF16>
+//   kPairArrive the P barriers are shared::cluster addresses in the leader CTA of a CTA pair (wide2 kernel)
+template <int kDP, bool kBF16, bool kPairArrive = false>
 __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
@@ -111,6 +112,9 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
       if (i >= lim) s[i] = -INFINITY;
   }
 
+  auto arrive = [](uint32_t bar) {
+    if constexpr (kPairArrive) mbar_arrive_cluster(bar); else mbar_arrive(bar);
+  };
   // p = 2^(s*c - m*c) for one group of 4 columns: kEmuPairs of every 8 element pairs go through
   // the FMA pipes (ex2_fma2), the rest through the MUFU
   auto exp4 = [&](int i, float nmc_) {
@@ -197,7 +201,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_early);
+    if (lane == 0) arrive(bar_early);
   }
   // ---- second half, with the row sum of the first half in the MUFU shadow
   float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
@@ -218,7 +222,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_mid);
+        if (lane == 0) arrive(bar_mid);
       }
     }
     if (kPvParts == 3) {
@@ -233,7 +237,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(bar_late);
+      arrive(bar_late);
       if (bar_turn != 0u) mbar_arrive(bar_turn);  // FA_SEQ: the other tile's softmax may start
     }
   }

@@ -239,6 +239,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// CTA-pair form: the data lands in THIS CTA's shared memory, the transaction bytes are counted on a
+// barrier that may live in the peer CTA (`bar_cluster` is a shared::cluster address, see mapa_shared)
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst_smem, const CUtensorMap* map,
+                                                 uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // 4-D tiled store smem -> global (bulk-group completion); out-of-bounds elements are not written
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0,
                                              int c1, int c2, int c3) {
@@ -329,8 +340,19 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+#ifndef FA_PAIR_ARRIVE_RELEASE
+#define FA_PAIR_ARRIVE_RELEASE 0
+#endif
+// Arrival on a barrier of (possibly) the peer CTA.  What the arrival publishes here is tensor-memory
+// state, ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync on this side and
+// tcgen05.fence::after_thread_sync on the waiter's, not generic-proxy memory, so the relaxed form is
+// enough; the release.cluster form is kept behind FA_PAIR_ARRIVE_RELEASE for comparison.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if FA_PAIR_ARRIVE_RELEASE
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),

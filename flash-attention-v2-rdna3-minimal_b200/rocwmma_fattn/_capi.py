@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = (
     "fa_launch_count",
     "fa_umma_selftest",
     "fa_umma2_selftest",
+    "fa_set_wide_pairs",
 )
 
 _I64x4 = ctypes.c_int64 * 4
@@ -88,6 +89,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_umma_selftest.restype = i
     lib.fa_umma2_selftest.argtypes = [vp, vp, vp, i, i, vp]
     lib.fa_umma2_selftest.restype = i
+    lib.fa_set_wide_pairs.argtypes = [i]
+    lib.fa_set_wide_pairs.restype = i
     if lib.fa_abi_version() != FA_ABI_VERSION:
         raise RuntimeError(
             f"{LIB_PATH}: ABI version {lib.fa_abi_version()} != expected {FA_ABI_VERSION}; rebuild"

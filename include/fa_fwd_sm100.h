@@ -127,6 +127,11 @@ const char* fa_last_error(void);
 /* FA_ABI_VERSION the library was built with. */
 int fa_abi_version(void);
 
+/* FA_KERNEL_WIDE at head dims 193..256, non-causal, runs on CTA pairs (thread-block cluster of two,
+ * tcgen05 cta_group::2: each SM fetches half of every K/V tile) unless disabled here (test / benchmarking
+ * hook).  Returns the previous setting. */
+int fa_set_wide_pairs(int enable);
+
 /* backward kernel selectors for fa_set_bwd_kernel() */
 #define FA_BWD_KERNEL_TC1 1    /* P and dS through shared memory (csrc/fa_bwd_tc.cuh); the default */
 #define FA_BWD_KERNEL_WS 2     /* warp-specialised, transposed scores, P^T / dS^T from TMEM (csrc/fa_bwd_ws.cuh) */
