@@ -39,7 +39,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
-std::atomic<int> g_wide_pairs{1};  // head dims 193..256, non-causal: CTA-pair kernel (fa_set_wide_pairs)
+std::atomic<int> g_wide_pairs{1};  // head dims 193..256: CTA-pair kernel (fa_set_wide_pairs)
 std::atomic<int> g_bwd_kernel{FA_BWD_KERNEL_TC1};  // measured faster than WS (tools/bench_bwd.py)
 #ifdef FA_TRACE
 unsigned long long* g_trace = nullptr;  // debug builds only (tools/trace_ws.py)
@@ -421,12 +421,12 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   return FA_OK;
 }
 
-// CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 256, non-causal
-template <bool kBF16>
+// CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 192 or 256
+template <int kDP, bool kBF16, bool kCausal>
 int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
   const Problem& p = pl.p;
-  auto kernel = fa::fa_fwd_wide2_kernel<kBF16>;
-  constexpr int smem = fa::Wide2Cfg::kTotal;
+  auto kernel = fa::fa_fwd_wide2_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::Wide2Cfg<kDP>::kTotal;
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
@@ -482,9 +482,14 @@ int launch_tc(int kernel, const Plan& pl, float* lse, cudaStream_t stream) {
     if (ca) return launch_wide<DP, false, true>(pl, lse, stream);             \
     return launch_wide<DP, false, false>(pl, lse, stream);                    \
   } while (0)
+    // CTA pairs pay where the one-CTA kernel is bound by shared-memory traffic: padded head dim 256
+    // (+14 %).  At 192 the pair kernel (Wide2Cfg<192> is supported and was measured) ties with the one-CTA
+    // kernel - 1563 vs 1577 TFLOPS, one softmax group is the limit there - so it is not instantiated.
+    if (p.D > 192 && g_wide_pairs.load(std::memory_order_relaxed)) {
+      if (bf) return ca ? launch_wide2<256, true, true>(pl, lse, stream) : launch_wide2<256, true, false>(pl, lse, stream);
+      return ca ? launch_wide2<256, false, true>(pl, lse, stream) : launch_wide2<256, false, false>(pl, lse, stream);
+    }
     if (p.D <= 192) FA_DISPATCH_WIDE(192);
-    if (!ca && g_wide_pairs.load(std::memory_order_relaxed))
-      return bf ? launch_wide2<true>(pl, lse, stream) : launch_wide2<false>(pl, lse, stream);
     FA_DISPATCH_WIDE(256);
   }
   if (kernel == FA_KERNEL_WIDE) {  // forced: the one-tile arrangement at head dims <= 128 (experiments)

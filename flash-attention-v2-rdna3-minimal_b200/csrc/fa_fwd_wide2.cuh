@@ -1,4 +1,4 @@
-// CTA-pair wide-head forward kernel ("wide2"): head dims 193..256, non-causal, on a thread-block
+// CTA-pair wide-head forward kernel ("wide2"): head dims 129..256, on a thread-block
 // cluster of TWO CTAs (two SMs) that share every K/V tile through tcgen05 cta_group::2.
 //
 // fa_fwd_wide.cuh at D = 256 is bound by shared-memory bandwidth and by its two-slot K/V ring: per KV
@@ -6,7 +6,7 @@
 // port against 2048 tensor cycles).  Here the pair computes one M = 256 product per MMA - each CTA owns
 // its 128 query rows (A operand, accumulators and P in its own tensor memory) and HALF of the B operand:
 //   S = Q K^T   : CTA r holds keys [64r, 64r+64) of the K tile   (half the rows of a K-major B)
-//   O += P V    : CTA r holds head-dim columns [128r, 128r+128) of the V tile   (half the columns)
+//   O += P V    : CTA r holds head-dim columns [D/2 r, D/2 r + D/2) of the V tile   (half the columns)
 // so each SM fetches and stores half of every K/V tile (64 KB instead of 128 KB per KV tile), reads
 // half of the B operand, and the ring holds four half-tiles instead of two whole ones.
 // umma2_probe.cuh pins the operand split on the hardware (tests: test_umma_cta_pair_selftest).
@@ -17,36 +17,42 @@
 //     their bytes there (cp.async.bulk.tensor ... cta_group::2) and both CTAs' softmax warps arrive there
 //     (mbarrier.arrive.shared::cluster), 16 warps per phase
 //   - "S ready", "K/V slot free", "PV done" signalled to both CTAs by one multicast tcgen05.commit
-// The two CTAs advance in lock step (same number of KV tiles: non-causal only).
+// The two CTAs advance in lock step: under a causal mask both visit the KV tiles of the later Q tile and
+// the earlier one sees its last tile fully masked.
 //
-// Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 for padded head dim 256.
+// Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 for padded head dims 192 and 256.
 #pragma once
 #include "fa_fwd_wide.cuh"
 
 namespace fa {
 
+template <int kDP_>
 struct Wide2Cfg {
-  static constexpr int kDP = 256;
-  static constexpr int kQBytes = kTileM * kDP * 2;         // 64 KB: my 128 query rows
-  static constexpr int kHalfBytes = kTileN * kDP;          // 32 KB: 64 keys x 256 (K) or 128 keys x 128 (V)
-  static constexpr int kStages = 4;                        // ring slots (one K half or one V half each)
+  static_assert(kDP_ == 192 || kDP_ == 256, "pair kernel: padded head dim 192 or 256");
+  static constexpr int kDP = kDP_;
+  static constexpr int kQBytes = kTileM * kDP * 2;         // my 128 query rows (64 KB at 256)
+  static constexpr int kKHalfBytes = (kTileN / 2) * kDP * 2;   // 64 keys x kDP: kDP/64 blocks of 8 KB
+  static constexpr int kVHalfBytes = 2 * kTileN * 64 * 2;      // 128 keys x kDP/2 columns in two 64-column blocks
+                                                               // (at kDP = 192 the second block is half used)
+  static constexpr int kSlotBytes = 32768;                 // one ring slot holds a K half or a V half
+  static constexpr int kStages = (kDP == 256) ? 4 : 5;
   static constexpr int kQ = 0;
   static constexpr int kKV = kQ + kQBytes;
-  static constexpr int kBars = kKV + kStages * kHalfBytes;
+  static constexpr int kBars = kKV + kStages * kSlotBytes;
   static constexpr int kNumBars = 11 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;   // float [2 parity][2 half][128]
   static constexpr int kFinal = kMax + 2 * 2 * 128 * 4;    // float [2 half][128] row sums
   static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
+  static_assert(kKHalfBytes <= kSlotBytes && kVHalfBytes <= kSlotBytes && kTotal <= 232448, "shared memory budget");
 };
 
-template <bool kBF16>
+template <int kDP, bool kBF16, bool kCausal>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
 fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                     const __grid_constant__ CUtensorMap tmap_k64,  // box {64 head-dim columns, 64 keys}
                     const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_o, const TcParams p) {
-  using C = Wide2Cfg;
-  constexpr int kDP = C::kDP;
+  using C = Wide2Cfg<kDP>;
   constexpr int kS = C::kStages;
   constexpr int kDBlocks = kDP / 64;
   constexpr int kKSteps = kDP / 16;
@@ -80,11 +86,17 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int qtile = blockIdx.x;  // the pair is (2p, 2p+1); the grid is padded to an even number of tiles
+  // the pair is Q tiles (2p, 2p+1); the grid is padded to an even number of tiles; causal: longest pairs first
+  const int pair = kCausal ? (static_cast<int>(gridDim.x / 2) - 1 - static_cast<int>(blockIdx.x / 2))
+                           : static_cast<int>(blockIdx.x / 2);
+  const int qtile = 2 * pair + static_cast<int>(rank);
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int row0 = qtile * kTileM;
-  const int n = (p.Nkv + kTileN - 1) / kTileN;  // KV tiles (the same for both CTAs: non-causal)
+  // KV tiles: the two CTAs advance in lock step, so under a causal mask both visit the tiles the LATER Q
+  // tile needs (2p + 2 of them); the extra tile is fully masked for the earlier one (P = 0, nothing added)
+  int n = (p.Nkv + kTileN - 1) / kTileN;
+  if (kCausal) n = min(n, 2 * pair + 2);
 
   auto idx_k = [](int j) { return j == 0 ? 0 : 2 * j - 1; };
   auto idx_v = [n](int j) { return (j + 1 < n) ? 2 * j + 2 : 2 * j + 1; };
@@ -135,17 +147,17 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       auto load = [&](bool is_v, int j, int idx) {
         const int slot = idx % kS;
         mbar_wait(bar_kv_empty(slot), ((idx / kS) & 1) ^ 1, 20);
-        if (leader) mbar_arrive_expect_tx(bar_kv_full(slot), 2 * C::kHalfBytes);
+        if (leader) mbar_arrive_expect_tx(bar_kv_full(slot), 2 * (is_v ? C::kVHalfBytes : C::kKHalfBytes));
         const uint32_t full_leader = mapa_shared(bar_kv_full(slot), 0);
-        const uint32_t dst = sKV + slot * C::kHalfBytes;
-        if (!is_v) {  // my 64 keys of K_j: four [64 keys x 64 columns] blocks, 8 KB apart
+        const uint32_t dst = sKV + slot * C::kSlotBytes;
+        if (!is_v) {  // my 64 keys of K_j: kDP/64 [64 keys x 64 columns] blocks, 8 KB apart
 #pragma unroll
           for (int db = 0; db < kDBlocks; ++db)
             tma_load_4d_2cta(dst + db * 8192, &tmap_k64, full_leader, db * 64, j * kTileN + rank * 64, h, b);
-        } else {      // my 128 head-dim columns of V_j: two [128 keys x 64 columns] blocks, 16 KB apart
+        } else {      // my kDP/2 head-dim columns of V_j: two [128 keys x 64 columns] blocks, 16 KB apart
 #pragma unroll
           for (int db = 0; db < 2; ++db)
-            tma_load_4d_2cta(dst + db * 16384, &tmap_v, full_leader, rank * 128 + db * 64, j * kTileN, h, b);
+            tma_load_4d_2cta(dst + db * 16384, &tmap_v, full_leader, rank * (kDP / 2) + db * 64, j * kTileN, h, b);
         }
       };
       load(false, 0, 0);
@@ -169,7 +181,7 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       auto issue_s = [&](int j) {  // S(j) = Q K_j^T for both CTAs into buffer j % 2
         const int idx = idx_k(j);
         wait_kv(idx);
-        const uint32_t kb = sKV + (idx % kS) * C::kHalfBytes;
+        const uint32_t kb = sKV + (idx % kS) * C::kSlotBytes;
 #pragma unroll
         for (int k = 0; k < kKSteps; ++k) {
           umma_ss_2cta(tmem + (j & 1) * 128,
@@ -184,7 +196,7 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int buf = j & 1;
         const uint32_t par = (j >> 1) & 1;
         wait_kv(idx);
-        const uint32_t vb = sKV + (idx % kS) * C::kHalfBytes;
+        const uint32_t vb = sKV + (idx % kS) * C::kSlotBytes;
         auto pv_step = [&](int ks, uint32_t acc) {
           umma_ts_2cta(tmem + kColO, tmem + buf * 128 + (ks >> 2) * 64 + (ks & 3) * 8,
                        make_smem_desc_sw128(vb + ks * 2048, 16384, 1024), idesc_o, acc);
@@ -257,7 +269,10 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
-      ws_softmax_step<kDP, kBF16, true>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv, false, c, m_run,
+      // causal: tile j >= qtile needs the mask; for j > qtile the row limit r + 1 - 128 (j - qtile) is <= 0,
+      // i.e. every key of the tile is hidden
+      ws_softmax_step<kDP, kBF16, true>(s, tS, tO, half, kCausal ? r - (j - qtile) * kTileN : r, lane,
+                                        j * kTileN + half * 64, p.Nkv, kCausal && j >= qtile, c, m_run,
                                         l_run, j > 0, my_max + buf * 256, other_max + buf * 256, pair_bar,
                                         p_early0 + buf * 8, p_late0 + buf * 8, 0u, p_mid0 + buf * 8, bar_o,
                                         static_cast<uint32_t>((j - 1) & 1));

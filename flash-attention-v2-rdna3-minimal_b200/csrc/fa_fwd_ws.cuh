@@ -77,6 +77,9 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 constexpr bool kSeq = FA_SEQ != 0;
 // P hand-off in 3 parts (32 + 16 + 16 keys per half; default) or 2 (32 + 32).  Measured: 3 parts are
 // +5.5 % at N=16384 and +7.7 % at N=4096 (the exposed tail of O += P V shrinks to two k-steps)
+#ifndef FA_EXP_SKIP_LOADS
+#define FA_EXP_SKIP_LOADS 0
+#endif
 #ifndef FA_PV_PARTS
 #define FA_PV_PARTS 3
 #endif
@@ -379,6 +382,15 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t use = idx / kS;
           mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
           FA_TR(4, idx >> 1, idx & 1);
+#if FA_EXP_SKIP_LOADS
+          // timing experiment only (wrong results): after the ring has been filled once, FA_EXP_SKIP_LOADS=1
+          // stops loading V tiles, =2 stops loading K and V tiles - how sensitive is the step to TMA /
+          // shared-memory-port traffic?
+          if (idx >= kS && (FA_EXP_SKIP_LOADS == 2 || (idx & 1))) {
+            mbar_arrive(bar_kv_full(slot));
+            continue;
+          }
+#endif
           mbar_arrive_expect_tx(bar_kv_full(slot), C::kTileBytes);
           const CUtensorMap* map = (idx & 1) ? &tmap_v : &tmap_k;
 #pragma unroll

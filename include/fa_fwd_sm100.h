@@ -127,7 +127,7 @@ const char* fa_last_error(void);
 /* FA_ABI_VERSION the library was built with. */
 int fa_abi_version(void);
 
-/* FA_KERNEL_WIDE at head dims 193..256, non-causal, runs on CTA pairs (thread-block cluster of two,
+/* FA_KERNEL_WIDE at head dims 193..256 runs on CTA pairs (thread-block cluster of two,
  * tcgen05 cta_group::2: each SM fetches half of every K/V tile) unless disabled here (test / benchmarking
  * hook).  Returns the previous setting. */
 int fa_set_wide_pairs(int enable);

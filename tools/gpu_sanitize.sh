@@ -24,8 +24,9 @@ import torch
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
 torch.manual_seed(0)
 # head dims 129..256: forward only (fa_fwd_wide_kernel), several KV tiles so the ring and both S buffers wrap
+# (head dims 193..256 run on CTA pairs: cluster of two, cta_group::2; 640 rows = 5 tiles = an odd, padded pair)
 for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 640, 640, 256, torch.float16, False), (1, 1, 300, 700, 160, torch.bfloat16, True),
-                                      (1, 1, 512, 512, 192, torch.float16, True)]:
+                                      (1, 1, 512, 512, 192, torch.float16, True), (1, 1, 640, 640, 232, torch.bfloat16, True)]:
     q, k, v = (torch.randn(B, H, n, D, dtype=dt, device="cuda") for n in (N, Nkv, Nkv))
     o = F.apply(q, k, v, None, causal)
     torch.cuda.synchronize()
