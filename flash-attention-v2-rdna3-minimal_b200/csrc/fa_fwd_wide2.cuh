@@ -23,19 +23,25 @@
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 for padded head dims 192 and 256.
 #pragma once
 #include "fa_fwd_wide.cuh"
+#include "wide_softmax.cuh"
+
+// 1: software-pipelined softmax steps (wide_softmax.cuh) - measured slower, see there
+#ifndef FA_WIDE2_PIPELINED
+#define FA_WIDE2_PIPELINED 0
+#endif
 
 namespace fa {
 
 template <int kDP_>
 struct Wide2Cfg {
-  static_assert(kDP_ == 192 || kDP_ == 256, "pair kernel: padded head dim 192 or 256");
+  static_assert(kDP_ == 64 || kDP_ == 128 || kDP_ == 192 || kDP_ == 256, "pair kernel: padded head dim");
   static constexpr int kDP = kDP_;
-  static constexpr int kQBytes = kTileM * kDP * 2;         // my 128 query rows (64 KB at 256)
+  static constexpr int kQBytes = kTileM * kDP * 2;             // my 128 query rows (64 KB at 256)
   static constexpr int kKHalfBytes = (kTileN / 2) * kDP * 2;   // 64 keys x kDP: kDP/64 blocks of 8 KB
-  static constexpr int kVHalfBytes = 2 * kTileN * 64 * 2;      // 128 keys x kDP/2 columns in two 64-column blocks
-                                                               // (at kDP = 192 the second block is half used)
-  static constexpr int kSlotBytes = 32768;                 // one ring slot holds a K half or a V half
-  static constexpr int kStages = (kDP == 256) ? 4 : 5;
+  static constexpr int kVBlocks = (kDP / 2 + 63) / 64;         // 64-column blocks holding my kDP/2 columns of V
+  static constexpr int kVHalfBytes = kVBlocks * kTileN * 64 * 2;   // (the last block is half used at 192 and 64)
+  static constexpr int kSlotBytes = kKHalfBytes > kVHalfBytes ? kKHalfBytes : kVHalfBytes;  // one ring slot
+  static constexpr int kStages = (kDP == 256) ? 4 : (kDP == 192) ? 5 : 8;
   static constexpr int kQ = 0;
   static constexpr int kKV = kQ + kQBytes;
   static constexpr int kBars = kKV + kStages * kSlotBytes;
@@ -43,7 +49,7 @@ struct Wide2Cfg {
   static constexpr int kMax = kBars + 8 * kNumBars + 16;   // float [2 parity][2 half][128]
   static constexpr int kFinal = kMax + 2 * 2 * 128 * 4;    // float [2 half][128] row sums
   static constexpr int kTotal = kFinal + 2 * 128 * 4 + 1024;  // + alignment slack
-  static_assert(kKHalfBytes <= kSlotBytes && kVHalfBytes <= kSlotBytes && kTotal <= 232448, "shared memory budget");
+  static_assert(kTotal <= 232448, "shared memory budget");
 };
 
 template <int kDP, bool kBF16, bool kCausal>
@@ -154,9 +160,9 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
           for (int db = 0; db < kDBlocks; ++db)
             tma_load_4d_2cta(dst + db * 8192, &tmap_k64, full_leader, db * 64, j * kTileN + rank * 64, h, b);
-        } else {      // my kDP/2 head-dim columns of V_j: two [128 keys x 64 columns] blocks, 16 KB apart
+        } else {      // my kDP/2 head-dim columns of V_j: [128 keys x 64 columns] blocks, 16 KB apart
 #pragma unroll
-          for (int db = 0; db < 2; ++db)
+          for (int db = 0; db < C::kVBlocks; ++db)
             tma_load_4d_2cta(dst + db * 16384, &tmap_v, full_leader, rank * (kDP / 2) + db * 64, j * kTileN, h, b);
         }
       };
@@ -259,6 +265,55 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_run = -INFINITY;
     float l_run = 0.f;
 
+#if FA_WIDE2_PIPELINED
+    // Software-pipelined steps (wide_softmax.cuh): the scores and the row maximum of tile j+1 are fetched
+    // during step j.  Two register arrays alternate between "current" and "next".
+    float sa[64], sb[64];
+    float mx_a = -INFINITY, mx_b = -INFINITY;
+    auto half_lim = [&](int j) {  // causal row limit of my half in tile j (<= 0: all hidden)
+      return r - (j - qtile) * kTileN + 1 - half * 64;
+    };
+    auto fetch = [&](float (&dst)[64], int j) {  // blocking: wait for S(j), load, mask, row maximum
+      return wide_fetch_tile(dst, tmem + lane_base + (j & 1) * 128 + half * 64, bar_s_full(j & 1), (j >> 1) & 1,
+                             j * kTileN + half * 64, p.Nkv, kCausal && j >= qtile, half_lim(j),
+                             my_max + (j & 1) * 256, other_max + (j & 1) * 256, pair_bar);
+    };
+    auto step = [&](float (&cur)[64], float (&nxt)[64], float mx_cur, float& mx_next, int j) {
+      const int buf = j & 1;
+      WideStepArgs a;
+      a.tS = tmem + lane_base + buf * 128 + half * 64;
+      a.tS_next = tmem + lane_base + (buf ^ 1) * 128 + half * 64;
+      a.tO = tO;
+      a.bar_early = p_early0 + buf * 8;
+      a.bar_mid = p_mid0 + buf * 8;
+      a.bar_late = p_late0 + buf * 8;
+      a.bar_s_next = bar_s_full(buf ^ 1);
+      a.s_next_parity = ((j + 1) >> 1) & 1;
+      a.bar_o = bar_o;
+      a.o_parity = static_cast<uint32_t>((j - 1) & 1);
+      a.has_next = j + 1 < n;
+      a.have_o = j > 0;
+      a.next_col0 = (j + 1) * kTileN + half * 64;
+      a.next_causal = kCausal && (j + 1 >= qtile);
+      a.next_r_lim_half = half_lim(j + 1);
+      a.Nkv = p.Nkv;
+      a.c = c;
+      a.my_max = my_max + ((j + 1) & 1) * 256;
+      a.other_max = other_max + ((j + 1) & 1) * 256;
+      a.pair_bar = pair_bar;
+      return wide_softmax_step<kDP, kBF16, true>(cur, nxt, mx_cur, mx_next, m_run, l_run, lane, a);
+    };
+    bool ready = false;  // tile j already fetched by the previous step?
+#pragma unroll 1
+    for (int j = 0; j < n; j += 2) {
+      if (!ready) mx_a = fetch(sa, j);
+      ready = step(sa, sb, mx_a, mx_b, j);
+      if (j + 1 < n) {
+        if (!ready) mx_b = fetch(sb, j + 1);
+        ready = step(sb, sa, mx_b, mx_a, j + 1);
+      }
+    }
+#else
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
       const int buf = j & 1;
@@ -277,6 +332,7 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                         p_early0 + buf * 8, p_late0 + buf * 8, 0u, p_mid0 + buf * 8, bar_o,
                                         static_cast<uint32_t>((j - 1) & 1));
     }
+#endif
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (my Q buffer) -> TMA store
     sFinal[half * 128 + r] = l_run;

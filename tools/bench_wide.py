@@ -50,6 +50,8 @@ def main():
     forced = os.environ.get("BENCH_KERNEL")
     if forced:
         _capi.set_kernel({v: k for k, v in _capi.KERNEL_NAMES.items()}[forced])
+    if os.environ.get("BENCH_PAIRS"):
+        _capi.lib.fa_set_wide_pairs(int(os.environ["BENCH_PAIRS"]))
     for dtype in (torch.float16, torch.bfloat16):
         for causal in (False, True):
             for D in DS:
