@@ -456,7 +456,8 @@ def main():
     dom_b, dom_n = points[-1]
     dom_ms = per_point_ms[-1]
     _st = (H * dom_n * D, dom_n * D, D, 1)
-    dom_kernel = {_capi.FA_KERNEL_SK: "fa_fwd_sk_kernel", _capi.FA_KERNEL_WS: "fa_fwd_ws_kernel"}.get(
+    dom_kernel = {_capi.FA_KERNEL_SK: "fa_fwd_sk_kernel", _capi.FA_KERNEL_WS: "fa_fwd_ws_kernel",
+                  _capi.FA_KERNEL_WS2: "fa_fwd_ws2_kernel (CTA pairs)"}.get(
         _capi.select_kernel(dom_b, H, dom_n, dom_n, D, _st, _st, _st, _st, _capi.FA_DTYPE_F16, False, D ** -0.5),
         "fa_fwd kernel")
     dom_flops = flops(dom_b, H, dom_n, D)

@@ -31,6 +31,7 @@
 #include "fa_fwd_sk.cuh"
 #include "fa_fwd_wide.cuh"
 #include "fa_fwd_wide2.cuh"
+#include "fa_fwd_ws2.cuh"
 #include "umma_probe.cuh"
 #include "umma2_probe.cuh"
 
@@ -190,6 +191,12 @@ int choose_kernel_shape(const Problem& p) {
   // and a shorter iteration (graph-timed, fp16 H=16 D=128: N=512 252 vs 179 TFLOPS, N=1024 654 vs 460;
   // at N=2048 - 256 tiles, two rounds - the two-tile kernel is back in front, 1081 vs 875).
   if (static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM) <= 148) return FA_KERNEL_WIDE;
+  // Long non-causal problems with many rounds: the two-tile kernel on CTA pairs (each SM fetches half of
+  // every K/V tile).  A/B on one box, fp16 H=16 D=128 N=16384: 1457-1461 vs 1441-1446 TFLOPS burst, 1250-1253 vs
+  // 1239-1241 sustained (+1 %); at N=4096 the lock step of the pair costs 3.6 %, so short KV loops stay put.
+  if (!p.causal && p.Nkv >= 8192 &&
+      static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) >= 4 * 148)
+    return FA_KERNEL_WS2;
   return FA_KERNEL_WS;
 }
 
@@ -203,7 +210,7 @@ struct Plan {
   Problem p;
   int device;
   CUtensorMap mq, mk, mv, mo;
-  CUtensorMap mk64;  // K with a 64-key box (CTA-pair kernel: each CTA loads half of a K tile); D > 192 only
+  CUtensorMap mk64;  // K with a 64-key box (CTA-pair kernel: each CTA loads half of a K tile)
   uint64_t stamp;
 };
 
@@ -240,7 +247,7 @@ struct PlanCache {
     if ((rc = make_map(&pl.mk, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.mv, v, p.B, p.H, p.Nkv, p.D, p.vs, p.dtype, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.mo, o, p.B, p.H, p.Nq, p.D, p.os, p.dtype, fa::kTileM))) return rc;
-    if (p.D > 192 && (rc = make_map(&pl.mk64, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN / 2))) return rc;
+    if ((rc = make_map(&pl.mk64, k, p.B, p.H, p.Nkv, p.D, p.ks, p.dtype, fa::kTileN / 2))) return rc;
     if (plans.size() < kCap) {
       plans.push_back(pl);
     } else {
@@ -421,6 +428,24 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   return FA_OK;
 }
 
+// two-tile kernel on CTA pairs (cluster of 2, cta_group::2): non-causal, head dims <= 128
+template <int kDP, bool kBF16>
+int launch_ws2(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_ws2_kernel<kDP, kBF16>;
+  constexpr int smem = fa::Ws2Cfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
+  const int blocks = (p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM);
+  dim3 grid((blocks + 1) & ~1, p.H, p.B);  // whole pairs
+  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 // CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 192 or 256
 template <int kDP, bool kBF16, bool kCausal>
 int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
@@ -451,6 +476,9 @@ int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t strea
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // not eligible / no workspace
     }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
+    case FA_KERNEL_WS2:
+      if constexpr (!kCausal) return launch_ws2<kDP, kBF16>(pl, lse, stream);
+      return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // the pair kernel is non-causal only
     case FA_KERNEL_TC1: return launch_tc1<kDP, kBF16, kCausal, false>(pl, lse, stream);
     case FA_KERNEL_TC1_PSMEM: return launch_tc1<kDP, kBF16, kCausal, true>(pl, lse, stream);
   }
@@ -702,7 +730,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WIDE) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS2) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 

@@ -56,6 +56,8 @@ extern "C" {
                                   block per SM; falls back to FA_KERNEL_WS otherwise */
 #define FA_KERNEL_WIDE 6       /* tcgen05, one Q tile per CTA with the score tile double-buffered: head dims
                                   129..256, and small causal problems at head dims <= 128 */
+#define FA_KERNEL_WS2 7        /* FA_KERNEL_WS on CTA pairs (cluster of two, cta_group::2): each SM fetches half of
+                                  every K/V tile; non-causal (causal requests run FA_KERNEL_WS) */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu

@@ -48,7 +48,7 @@ def _st(B, H, N, D):
     [
         ((1, 16, 8192, 8192, 128), _capi.FA_KERNEL_SK),       # BASELINE sweep point: 512 blocks >= 2 x 148 SMs
         ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # 256 blocks < 2 per SM: one-shot kernel
-        ((1, 16, 16384, 16384, 128), _capi.FA_KERNEL_WS),     # 1024 blocks = 6.92 rounds: 1.2 % lost, one-shot
+        ((1, 16, 16384, 16384, 128), _capi.FA_KERNEL_WS2),    # 1024 blocks = 6.92 rounds, long KV loop: two-tile kernel on CTA pairs
         ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),      # BASELINE config 5: 110.7 rounds, one-shot
         ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
         ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad

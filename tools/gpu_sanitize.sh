@@ -32,6 +32,17 @@ for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 640, 640, 256, torch.float16, False
     torch.cuda.synchronize()
     print("ok", B, H, N, Nkv, D, dt, causal, float(o.float().mean()))
 PY
+cat >> /tmp/san_wide.py <<'PY'
+# the two-tile kernel on CTA pairs (forced: auto picks it for long non-causal problems only)
+from rocwmma_fattn import _capi
+_capi.set_kernel(_capi.FA_KERNEL_WS2)
+for (B, H, N, Nkv, D, dt) in [(1, 2, 768, 640, 128, torch.float16), (1, 1, 300, 900, 64, torch.bfloat16)]:
+    q, k, v = (torch.randn(B, H, n, D, dtype=dt, device="cuda") for n in (N, Nkv, Nkv))
+    o = F.apply(q, k, v, None, False)
+    torch.cuda.synchronize()
+    print("ok ws2", B, H, N, Nkv, D, dt, float(o.float().mean()))
+_capi.set_kernel(_capi.FA_KERNEL_AUTO)
+PY
 if [ -n "$SAN_ONLY_WIDE" ]; then cp /tmp/san_wide.py /tmp/san.py; else cat /tmp/san_wide.py >> /tmp/san.py; fi
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=fa_ python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1
