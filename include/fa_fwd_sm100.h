@@ -55,7 +55,8 @@ extern "C" {
                                   (query block, KV tile) items; non-causal, Nq % 256 == 0, >= 1 query
                                   block per SM; falls back to FA_KERNEL_WS otherwise */
 #define FA_KERNEL_WIDE 6       /* tcgen05, one Q tile per CTA with the score tile double-buffered: head dims
-                                  129..256, and small causal problems at head dims <= 128 */
+                                  129..256 (on CTA pairs above 192), and small or short-causal problems at head
+                                  dims <= 128 */
 #define FA_KERNEL_WS2 7        /* FA_KERNEL_WS on CTA pairs (cluster of two, cta_group::2): each SM fetches half of
                                   every K/V tile; non-causal (causal requests run FA_KERNEL_WS) */
 
