@@ -684,6 +684,45 @@ int run_device(const void* q, const void* k, const void* v, void* o, float* lse,
 }
 
 // ---------------------------------------------------------------------------------------------
+// host-buffer path: chunk planner (pure host logic, exported as fa_host_plan_chunks for the CPU tests)
+// ---------------------------------------------------------------------------------------------
+// Heads per chunk of the pipelined H2D -> kernel -> D2H path over the flattened (b,h) axis.  The H2D stream
+// is busy from the first byte to the last, so a call takes
+//   T(n) = H2D_total + n * c_issue + (compute_total + D2H_total) / n
+// (the tail of the last chunk is all that is not hidden; c_issue = the ~10 runtime calls a chunk costs on
+// the host, ~40 us measured on B200 boxes: tools/e2e_probe.py).  n = sqrt(tail / c_issue) minimises it: 1 chunk
+// at N=512, 8 at N=16384 for the sweep.  Then the last chunk is halved while that shortens the exposed tail
+// (its kernel + its D2H) by more than the ~25 us of copy start-up and event hand-offs an extra chunk costs on
+// the device; a CTA's run time is set by Nkv alone (~1.6 us per 128-key tile), so the kernel term stops
+// shrinking once the chunk no longer fills the SMs.  FA_HOST_CHUNKS=n overrides the count (no tail split;
+// "0" = planner count without the tail split).
+std::vector<size_t> plan_host_chunks(size_t heads, int Nq, int Nkv, int D, int causal) {
+  std::vector<size_t> chunk_heads;
+  const size_t q_head = size_t(Nq) * D * 2;
+  const double flops = 4.0 * double(heads) * Nq * Nkv * D * (causal ? 0.5 : 1.0);
+  const double tail_us = flops / 1.0e9 + double(heads * q_head) / 50.0e3 + 12.0;
+  double n = std::sqrt(tail_us / 40.0);
+  const char* e = std::getenv("FA_HOST_CHUNKS");
+  if (e != nullptr && std::atof(e) > 0) n = std::atof(e);
+  size_t nc = n < 1.0 ? 1 : static_cast<size_t>(n + 0.5);
+  if (nc > heads) nc = heads;
+  const size_t hg = (heads + nc - 1) / nc;
+  for (size_t h0 = 0; h0 < heads; h0 += hg) chunk_heads.push_back(h0 + hg <= heads ? hg : heads - h0);
+  auto tail = [&](size_t nh) {
+    const double cta_us = 10.0 + 1.6 * double((Nkv + 127) / 128) * (causal ? 0.5 : 1.0);
+    const double waves = std::ceil(double(nh) * double((Nq + 255) / 256) / 148.0);
+    return cta_us * waves + double(nh * q_head) / 50.0e3;
+  };
+  while (e == nullptr && chunk_heads.back() >= 2 &&
+         tail(chunk_heads.back()) - tail(chunk_heads.back() / 2) > 25.0) {
+    const size_t last = chunk_heads.back();
+    chunk_heads.back() = last - last / 2;
+    chunk_heads.push_back(last / 2);
+  }
+  return chunk_heads;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-buffer path: per-device workspace + three streams
 // ---------------------------------------------------------------------------------------------
 struct HostWs {
@@ -732,6 +771,14 @@ uint64_t fa_launch_count(void) { return g_launches.load(); }
 int fa_set_kernel(int kernel) {
   if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS2) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
+}
+
+int fa_host_plan_chunks(int B, int H, int Nq, int Nkv, int D, int causal, int* out, int cap) {
+  if (B < 1 || H < 1 || Nq < 1 || Nkv < 1 || D < 1 || out == nullptr || cap < 1)
+    return -fail(FA_ERR_INVALID_ARG, "fa_host_plan_chunks: bad argument");
+  const std::vector<size_t> c = plan_host_chunks(size_t(B) * H, Nq, Nkv, D, causal);
+  for (size_t i = 0; i < c.size() && i < size_t(cap); ++i) out[i] = static_cast<int>(c[i]);
+  return static_cast<int>(c.size());
 }
 
 int fa_set_wide_pairs(int enable) { return g_wide_pairs.exchange(enable ? 1 : 0); }
@@ -818,39 +865,8 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
     w.cap_lse = bytes_lse;
   }
 
-  // Chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D].  The
-  // H2D stream is busy from the first byte to the last, so the call takes
-  //   T(n) = H2D_total + n * c_issue + (compute_total + D2H_total) / n
-  // (the tail of the last chunk is all that is not hidden; c_issue = the ~10 runtime calls a chunk
-  // costs on the host, ~40 us measured on B200 boxes: tools/e2e_probe.py).  n = sqrt(tail / c_issue)
-  // minimises it: 1 chunk at N=512 (was 8: 0.72 ms -> see profiles/r01_e2e_probe.txt), 8 at N=16384.
-  std::vector<size_t> chunk_heads;
-  {
-    const double flops = 4.0 * double(heads) * Nq * Nkv * D * (causal ? 0.5 : 1.0);
-    const double tail_us = flops / 1.0e9 + double(bytes_q) / 50.0e3 + 12.0;
-    double n = std::sqrt(tail_us / 40.0);
-    const char* e = std::getenv("FA_HOST_CHUNKS");
-    if (e != nullptr && std::atof(e) > 0) n = std::atof(e);  // "0": planner count, no tail split
-    size_t nc = n < 1.0 ? 1 : static_cast<size_t>(n + 0.5);
-    if (nc > heads) nc = heads;
-    const size_t hg = (heads + nc - 1) / nc;
-    for (size_t h0 = 0; h0 < heads; h0 += hg) chunk_heads.push_back(h0 + hg <= heads ? hg : heads - h0);
-    // Halve the last chunk while that shortens the exposed tail (its kernel + its D2H) by more than
-    // the ~25 us of copy start-up and event hand-offs an extra chunk costs on the device.  A CTA's
-    // run time is set by Nkv alone (~1.6 us per 128-key tile), so the kernel term stops shrinking
-    // once the chunk no longer fills the SMs.
-    auto tail = [&](size_t nh) {
-      const double cta_us = 10.0 + 1.6 * double((Nkv + 127) / 128) * (causal ? 0.5 : 1.0);
-      const double waves = std::ceil(double(nh) * double((Nq + 255) / 256) / 148.0);
-      return cta_us * waves + double(nh * q_head) / 50.0e3;
-    };
-    while (e == nullptr && chunk_heads.back() >= 2 &&
-           tail(chunk_heads.back()) - tail(chunk_heads.back() / 2) > 25.0) {
-      const size_t last = chunk_heads.back();
-      chunk_heads.back() = last - last / 2;
-      chunk_heads.push_back(last / 2);
-    }
-  }
+  // chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D]
+  const std::vector<size_t> chunk_heads = plan_host_chunks(heads, Nq, Nkv, D, causal);
   const size_t n_chunks = chunk_heads.size();
   while (w.ev_in.size() < n_chunks) {
     cudaEvent_t e1, e2;

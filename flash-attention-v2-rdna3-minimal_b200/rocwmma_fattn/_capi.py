@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "fa_umma_selftest",
     "fa_umma2_selftest",
     "fa_set_wide_pairs",
+    "fa_host_plan_chunks",
 )
 
 _I64x4 = ctypes.c_int64 * 4
@@ -93,6 +94,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_umma2_selftest.restype = i
     lib.fa_set_wide_pairs.argtypes = [i]
     lib.fa_set_wide_pairs.restype = i
+    lib.fa_host_plan_chunks.argtypes = [i, i, i, i, i, i, ctypes.POINTER(ctypes.c_int), i]
+    lib.fa_host_plan_chunks.restype = i
     if lib.fa_abi_version() != FA_ABI_VERSION:
         raise RuntimeError(
             f"{LIB_PATH}: ABI version {lib.fa_abi_version()} != expected {FA_ABI_VERSION}; rebuild"
@@ -131,6 +134,15 @@ def strides4(st) -> "ctypes.Array":
             _STRIDES_CACHE.clear()
         arr = _STRIDES_CACHE[key] = _I64x4(int(st[0]), int(st[1]), int(st[2]), int(st[3]))
     return arr
+
+
+def host_plan_chunks(B, H, Nq, Nkv, D, causal=False):
+    """Heads per pipeline chunk fa_fwd_sm100_host() would use for this problem (pure host logic)."""
+    buf = (ctypes.c_int * 4096)()
+    n = lib.fa_host_plan_chunks(B, H, Nq, Nkv, D, int(bool(causal)), buf, 4096)
+    if n < 0:
+        raise FlashAttnError(-n, "fa_host_plan_chunks")
+    return [buf[k] for k in range(min(n, 4096))]
 
 
 def last_error() -> str:

@@ -121,6 +121,13 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
                  const int64_t dk_strides[4], const int64_t dv_strides[4], int dtype, int causal,
                  float scale, void* stream);
 
+/*
+ * How fa_fwd_sm100_host() would split the flattened (batch, head) axis of this problem into pipeline chunks:
+ * writes up to `cap` chunk sizes (heads per chunk, in order) to `out` and returns the number of chunks (their
+ * sizes sum to B*H), or a negative error code.  Pure host logic: usable without a GPU.
+ */
+int fa_host_plan_chunks(int B, int H, int Nq, int Nkv, int D, int causal, int* out, int cap);
+
 /* Release the device workspace and streams fa_fwd_sm100_host() caches for the current device. */
 int fa_host_workspace_release(void);
 

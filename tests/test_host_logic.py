@@ -108,3 +108,32 @@ def test_sdpa_front_end_is_strict_and_installable():
     finally:
         sdpa.uninstall()
     assert torch.nn.functional.scaled_dot_product_attention is stock
+
+
+def test_host_chunk_planner_covers_every_head_and_follows_its_cost_model(monkeypatch):
+    """fa_fwd_sm100_host() pipelines H2D -> kernel -> D2H over chunks of whole heads; the planner is pure
+    host logic (fa_host_plan_chunks).  Sizes must sum to B*H, the count grows with the work that can be
+    hidden, and only the tail is shortened."""
+    from rocwmma_fattn import _capi
+
+    monkeypatch.delenv("FA_HOST_CHUNKS", raising=False)
+    counts = {}
+    for n in (512, 1024, 2048, 4096, 8192, 16384):
+        c = _capi.host_plan_chunks(1, 16, n, n, 128)
+        assert sum(c) == 16 and min(c) >= 1
+        assert c == sorted(c, reverse=True)  # uniform chunks, then a shrinking tail
+        counts[n] = len(c)
+    assert counts[512] == 1                       # launch-bound: one chunk, no pipeline overhead
+    assert counts[16384] >= 8                     # PCIe-bound: enough chunks to hide kernel and D2H
+    assert all(counts[a] <= counts[b] for a, b in zip((512, 1024, 2048, 4096, 8192), (1024, 2048, 4096, 8192, 16384)))
+    # ragged head counts and a single head
+    for heads in (1, 3, 5, 7, 1024):
+        c = _capi.host_plan_chunks(1, heads, 4096, 4096, 128, causal=True)
+        assert sum(c) == heads and min(c) >= 1
+    # explicit override: uniform, no tail split
+    monkeypatch.setenv("FA_HOST_CHUNKS", "4")
+    assert _capi.host_plan_chunks(1, 16, 16384, 16384, 128) == [4, 4, 4, 4]
+    monkeypatch.setenv("FA_HOST_CHUNKS", "64")
+    assert _capi.host_plan_chunks(1, 16, 512, 512, 128) == [1] * 16
+    with pytest.raises(_capi.FlashAttnError):
+        _capi.host_plan_chunks(0, 16, 512, 512, 128)
