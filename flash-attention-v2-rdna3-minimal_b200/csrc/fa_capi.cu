@@ -32,6 +32,7 @@
 #include "fa_fwd_wide.cuh"
 #include "fa_fwd_wide2.cuh"
 #include "fa_fwd_ws2.cuh"
+#include "fa_fwd_quad2.cuh"
 #include "umma_probe.cuh"
 #include "umma2_probe.cuh"
 
@@ -428,6 +429,24 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   return FA_OK;
 }
 
+// one-tile kernel on CTA pairs with four threads per query row: head dims <= 128
+template <int kDP, bool kBF16, bool kCausal>
+int launch_quad2(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_quad2_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::Quad2Cfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
+  const int tiles = (p.Nq + fa::kTileM - 1) / fa::kTileM;
+  dim3 grid((tiles + 1) & ~1, p.H, p.B);
+  kernel<<<grid, fa::kQuadThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 // two-tile kernel on CTA pairs (cluster of 2, cta_group::2): non-causal, head dims <= 128
 template <int kDP, bool kBF16>
 int launch_ws2(const Plan& pl, float* lse, cudaStream_t stream) {
@@ -476,6 +495,7 @@ int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t strea
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // not eligible / no workspace
     }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
+    case FA_KERNEL_QUAD2: return launch_quad2<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_WS2:
       if constexpr (!kCausal) return launch_ws2<kDP, kBF16>(pl, lse, stream);
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // the pair kernel is non-causal only
@@ -769,7 +789,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS2) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_QUAD2) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 

@@ -20,6 +20,7 @@ FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0
 FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS, FA_KERNEL_SK = 0, 1, 2, 3, 4, 5
 FA_KERNEL_WIDE = 6
 FA_KERNEL_WS2 = 7
+FA_KERNEL_QUAD2 = 8
 FA_BWD_KERNEL_TC1, FA_BWD_KERNEL_WS = 1, 2
 KERNEL_NAMES = {
     FA_KERNEL_AUTO: "auto",
@@ -30,6 +31,7 @@ KERNEL_NAMES = {
     FA_KERNEL_SK: "sk",
     FA_KERNEL_WIDE: "wide",
     FA_KERNEL_WS2: "ws2",
+    FA_KERNEL_QUAD2: "quad2",
 }
 
 # every symbol include/fa_fwd_sm100.h declares

@@ -59,6 +59,8 @@ extern "C" {
                                   dims <= 128 */
 #define FA_KERNEL_WS2 7        /* FA_KERNEL_WS on CTA pairs (cluster of two, cta_group::2): each SM fetches half of
                                   every K/V tile; non-causal (causal requests run FA_KERNEL_WS) */
+#define FA_KERNEL_QUAD2 8      /* one Q tile per CTA on CTA pairs, double-buffered S, FOUR threads per query row
+                                  (16 softmax warps on the one tile); head dims <= 128 */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu
