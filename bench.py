@@ -392,15 +392,15 @@ def main():
         (g, _keep), reps = per_graphs[n]
         g.replay()
         torch.cuda.synchronize()
-        best = float("inf")
-        for _ in range(3):
+        samples = []
+        for _ in range(5):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             g.replay()
             a1.record()
             torch.cuda.synchronize()
-            best = min(best, a0.elapsed_time(a1) / reps)
-        per_point_ms.append(best)
+            samples.append(a0.elapsed_time(a1) / reps)
+        per_point_ms.append(sorted(samples)[len(samples) // 2])  # median: the SM clock moves under the power cap
 
     # clocks: the timed region can be shorter than one nvidia-smi period, so keep replaying the same
     # graph (untimed) for ~0.4 s and report the clocks of both windows
@@ -454,7 +454,10 @@ def main():
 
     # ---- roofline of the dominant kernel (largest N of the step), per launch, one GPU's share
     dom_b, dom_n = points[-1]
-    dom_ms = per_point_ms[-1]
+    # average duration of the dominant launch INSIDE the timed region = the step time measured there x the
+    # launch's share of a step (shares from the per-sequence-length graphs); the isolated figure is kept too
+    dom_ms_isolated = per_point_ms[-1]
+    dom_ms = (total_ms / args.steps) * per_point_ms[-1] / sum(per_point_ms)
     _st = (H * dom_n * D, dom_n * D, D, 1)
     dom_kernel = {_capi.FA_KERNEL_SK: "fa_fwd_sk_kernel", _capi.FA_KERNEL_WS: "fa_fwd_ws_kernel",
                   _capi.FA_KERNEL_WS2: "fa_fwd_ws2_kernel (CTA pairs)"}.get(
@@ -466,6 +469,8 @@ def main():
                 "frac": round(achieved / peaks["tflops"], 4), "traffic": None,
                 "kernel": f"{dom_kernel}<128,f16,non-causal> B={dom_b} H=16 N={dom_n}",
                 "flops_per_launch": dom_flops, "ms_per_launch": round(dom_ms, 5),
+                "ms_per_launch_isolated": round(dom_ms_isolated, 5),
+                "share_of_step": round(per_point_ms[-1] / sum(per_point_ms), 4),
                 "peak_source": peaks["source"],
                 "frac_of_sustained": round(achieved / peaks["tflops_sustained"], 4) if peaks["tflops_sustained"] else None,
                 "algorithmic_bytes_per_launch": 8.0 * dom_b * H * dom_n * D,

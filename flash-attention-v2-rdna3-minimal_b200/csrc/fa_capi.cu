@@ -195,7 +195,8 @@ int choose_kernel_shape(const Problem& p) {
   // Long non-causal problems with many rounds: the two-tile kernel on CTA pairs (each SM fetches half of
   // every K/V tile).  A/B on one box, fp16 H=16 D=128 N=16384: 1457-1461 vs 1441-1446 TFLOPS burst, 1250-1253 vs
   // 1239-1241 sustained (+1 %); at N=4096 the lock step of the pair costs 3.6 %, so short KV loops stay put.
-  if (!p.causal && p.Nkv >= 8192 &&
+  static const bool no_ws2 = std::getenv("FA_NO_WS2") != nullptr;  // A/B switch for whole-bench comparisons
+  if (!no_ws2 && !p.causal && p.Nkv >= 8192 &&
       static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) >= 4 * 148)
     return FA_KERNEL_WS2;
   return FA_KERNEL_WS;
