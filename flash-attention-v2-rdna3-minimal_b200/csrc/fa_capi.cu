@@ -33,6 +33,7 @@
 #include "fa_fwd_wide2.cuh"
 #include "fa_fwd_ws2.cuh"
 #include "fa_fwd_quad2.cuh"
+#include "fa_fwd_ws3.cuh"
 #include "umma_probe.cuh"
 #include "umma2_probe.cuh"
 
@@ -466,6 +467,24 @@ int launch_ws2(const Plan& pl, float* lse, cudaStream_t stream) {
   return FA_OK;
 }
 
+// two-tile kernel on CTA pairs with P through shared memory (S_t(j+1) issued ahead of PV_t(j)): non-causal
+template <int kDP, bool kBF16>
+int launch_ws3(const Plan& pl, float* lse, cudaStream_t stream) {
+  const Problem& p = pl.p;
+  auto kernel = fa::fa_fwd_ws3_kernel<kDP, kBF16>;
+  constexpr int smem = fa::Ws3Cfg<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, pl.device);
+  if (rc) return rc;
+  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
+  const int blocks = (p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM);
+  dim3 grid((blocks + 1) & ~1, p.H, p.B);
+  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 // CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 192 or 256
 template <int kDP, bool kBF16, bool kCausal>
 int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
@@ -497,6 +516,9 @@ int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t strea
     }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_QUAD2: return launch_quad2<kDP, kBF16, kCausal>(pl, lse, stream);
+    case FA_KERNEL_WS3:
+      if constexpr (!kCausal) return launch_ws3<kDP, kBF16>(pl, lse, stream);
+      return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // non-causal only
     case FA_KERNEL_WS2:
       if constexpr (!kCausal) return launch_ws2<kDP, kBF16>(pl, lse, stream);
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // the pair kernel is non-causal only
@@ -790,7 +812,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_QUAD2) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS3) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 

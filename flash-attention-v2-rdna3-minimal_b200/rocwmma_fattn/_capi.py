@@ -21,6 +21,7 @@ FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS
 FA_KERNEL_WIDE = 6
 FA_KERNEL_WS2 = 7
 FA_KERNEL_QUAD2 = 8
+FA_KERNEL_WS3 = 9
 FA_BWD_KERNEL_TC1, FA_BWD_KERNEL_WS = 1, 2
 KERNEL_NAMES = {
     FA_KERNEL_AUTO: "auto",
@@ -32,6 +33,7 @@ KERNEL_NAMES = {
     FA_KERNEL_WIDE: "wide",
     FA_KERNEL_WS2: "ws2",
     FA_KERNEL_QUAD2: "quad2",
+    FA_KERNEL_WS3: "ws3",
 }
 
 # every symbol include/fa_fwd_sm100.h declares
