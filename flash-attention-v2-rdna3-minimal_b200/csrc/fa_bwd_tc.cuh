@@ -26,6 +26,14 @@
 
 namespace fa {
 
+// Of every 4 pairs of P elements, how many compute 2^x on the FMA pipes instead of the MUFU (backward).
+// Measured (fp16, D=128, N=16384 / 4096): 0 -> 685 / 557 TFLOPS, 1 -> 669 / 546, 2 -> 660 / 537: the MUFU is not
+// what bounds the P / dS pass (its shared-memory stores and the TMEM round trips are), so the default is 0.
+#ifndef FA_BWD_EMU_PAIRS
+#define FA_BWD_EMU_PAIRS 0
+#endif
+constexpr int kBwdEmuPairs = FA_BWD_EMU_PAIRS;
+
 struct BwdParams {
   const float* lse;    // [B,H,Nq] base-2 log-sum-exp of the scaled scores (forward output)
   const float* delta;  // [B,H,Nq] rowsum(dO o O), fp32 (fa_bwd_delta_kernel)
@@ -248,8 +256,22 @@ fa_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_wait_ld();
       float pf[32], df[32];
 #pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        // P = 2^(S c - L): kBwdEmuPairs of every 4 element pairs on the FMA pipes (ex2_fma2), the rest on the
+        // MUFU, which is the busiest pipe of this phase (64 exponentials per thread, 16 per clock per SM)
+        float x0 = fmaf(__uint_as_float(sv[e]), c, nl), x1 = fmaf(__uint_as_float(sv[e + 1]), c, nl);
+        if (((e >> 1) & 3) < kBwdEmuPairs) {
+          ex2_fma2(x0, x1);
+        } else {
+          x0 = ex2_approx(x0);
+          x1 = ex2_approx(x1);
+        }
+        pf[e] = x0;
+        pf[e + 1] = x1;
+      }
+#pragma unroll
       for (int e = 0; e < 32; ++e) {
-        float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c, nl));
+        float pe = pf[e];
         if (need_mask) {
           const int key = key0 + cb + e;
           const bool ok = row_ok && key < p.Nkv && (!kCausal || key <= row);
