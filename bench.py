@@ -292,7 +292,10 @@ def main():
 
     from rocwmma_fattn import _capi
     from rocwmma_fattn.FlashAttn import FlashAttentionFunction, flash_attn_forward_host
-    from shard import shard_batch
+    from shard import bind_to_device_numa, shard_batch
+
+    # one process per GPU: keep this rank's threads and the pinned buffers it allocates on the GPU's NUMA node
+    numa_cpus = bind_to_device_numa(local_rank) if world > 1 and not os.environ.get("FA_NO_NUMA_BIND") else []
 
     fa = FlashAttentionFunction.apply
     peaks = load_peaks()
@@ -534,7 +537,8 @@ def main():
                    "ms_per_step": round(e2e_s * 1e3, 4), "steps": e2e_steps,
                    "api": "rocwmma_fattn.FlashAttn.flash_attn_forward_host -> fa_fwd_sm100_host (pinned host "
                           "Q,K,V in, pinned host O out, copies inside the timed region, wall clock)",
-                   "pcie_gbs": round((h2d + d2h) / e2e_s / 1e9, 1)}
+                   "pcie_gbs": round((h2d + d2h) / e2e_s / 1e9, 1),
+                   "numa_bound_cpus": len(numa_cpus)}
     # sanity: the e2e path produced the same bits as the device path for the last point
     del host
 

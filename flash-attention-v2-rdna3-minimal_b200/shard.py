@@ -35,3 +35,43 @@ def aggregate_tflops(flops_all_ranks: float, local_ms: float, dist=None, device=
     """Whole-job TFLOPS = FLOPs of all ranks / max-over-ranks time."""
     ms = reduce_max_time(local_ms, dist, device)
     return flops_all_ranks / (ms * 1e-3) / 1e12
+
+
+def device_local_cpus(pci_domain: int, pci_bus: int, pci_device: int, sysfs: str = "/sys/bus/pci/devices") -> list[int]:
+    """CPUs on the NUMA node the GPU hangs off (``local_cpulist`` of its PCI device), or [] if unknown."""
+    path = f"{sysfs}/{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0/local_cpulist"
+    try:
+        with open(path) as fh:
+            text = fh.read().strip()
+    except OSError:
+        return []
+    cpus: list[int] = []
+    for part in text.split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_device_numa(device_index: int) -> list[int]:
+    """Pin the calling process to the CPUs local to GPU ``device_index`` so that the pinned host buffers it
+    allocates afterwards (first touch) and the threads that feed the copy engines sit on the GPU's NUMA node.
+    One process per GPU: without this, ranks on a two-socket host stage half of their PCIe traffic through the
+    inter-socket link.  Returns the CPU list it bound to ([] = left unchanged: unknown topology, or the local
+    list is not a subset of what the process may use)."""
+    import os
+
+    import torch
+
+    prop = torch.cuda.get_device_properties(device_index)
+    cpus = device_local_cpus(prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+    try:
+        allowed = os.sched_getaffinity(0)
+    except AttributeError:
+        return []
+    cpus = [c for c in cpus if c in allowed]
+    if not cpus or len(cpus) == len(allowed):
+        return []
+    os.sched_setaffinity(0, cpus)
+    return cpus

@@ -137,3 +137,16 @@ def test_host_chunk_planner_covers_every_head_and_follows_its_cost_model(monkeyp
     assert _capi.host_plan_chunks(1, 16, 512, 512, 128) == [1] * 16
     with pytest.raises(_capi.FlashAttnError):
         _capi.host_plan_chunks(0, 16, 512, 512, 128)
+
+
+def test_device_local_cpus_parses_sysfs(tmp_path):
+    """shard.device_local_cpus reads the GPU's PCI device node (local_cpulist) to find its NUMA-local CPUs."""
+    import shard
+
+    d = tmp_path / "0000:1b:00.0"
+    d.mkdir()
+    (d / "local_cpulist").write_text("0-3,32-35\n")
+    assert shard.device_local_cpus(0, 0x1B, 0, sysfs=str(tmp_path)) == [0, 1, 2, 3, 32, 33, 34, 35]
+    assert shard.device_local_cpus(0, 0x1C, 0, sysfs=str(tmp_path)) == []
+    (d / "local_cpulist").write_text("7\n")
+    assert shard.device_local_cpus(0, 0x1B, 0, sysfs=str(tmp_path)) == [7]
