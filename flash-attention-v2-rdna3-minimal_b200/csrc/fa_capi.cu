@@ -775,8 +775,9 @@ struct HostWs {
   float* dlse = nullptr;
   size_t cap_q = 0, cap_kv = 0, cap_lse = 0;
   std::vector<cudaEvent_t> ev_in, ev_run;
+  std::mutex mu;  // one host call at a time per device (the workspace and its streams are per device);
+                  // calls on different devices - the multi-GPU shard driven from one process - run concurrently
 };
-std::mutex g_ws_mu;
 HostWs g_ws[64];
 
 int ws_release(HostWs& w) {
@@ -790,7 +791,13 @@ int ws_release(HostWs& w) {
   if (w.s_in) cudaStreamDestroy(w.s_in);
   if (w.s_run) cudaStreamDestroy(w.s_run);
   if (w.s_out) cudaStreamDestroy(w.s_out);
-  w = HostWs();
+  w.init = false;  // (not `w = HostWs()`: the mutex the caller holds lives in w)
+  w.s_in = w.s_run = w.s_out = nullptr;
+  w.dq = w.dk = w.dv = w.dout = nullptr;
+  w.dlse = nullptr;
+  w.cap_q = w.cap_kv = w.cap_lse = 0;
+  w.ev_in.clear();
+  w.ev_run.clear();
   return FA_OK;
 }
 
@@ -873,8 +880,8 @@ int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, floa
   if ((rc = check_device(&dev))) return rc;
   if (dev >= 64) return fail(FA_ERR_UNSUPPORTED, "device ordinal >= 64");
 
-  std::lock_guard<std::mutex> lk(g_ws_mu);
   HostWs& w = g_ws[dev];
+  std::lock_guard<std::mutex> lk(w.mu);
   if (!w.init) {
     FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
     FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
@@ -1071,7 +1078,7 @@ int fa_host_workspace_release(void) {
   int rc = check_device(&dev);
   if (rc) return rc;
   if (dev >= 64) return FA_OK;
-  std::lock_guard<std::mutex> lk(g_ws_mu);
+  std::lock_guard<std::mutex> lk(g_ws[dev].mu);
   return ws_release(g_ws[dev]);
 }
 
