@@ -579,6 +579,21 @@ def main():
                                  "tflops": round(flops(1, H, n, d_head) / (ms * 1e-3) / 1e12, 2)}
             del pool
         extras["f16_noncausal_head_dims_above_128"] = wide
+        # context only, NOT this repo's code: the library kernel torch dispatches to for the same call on this box
+        # (cuDNN fused attention at head dim 128).  It is the bar DESIGN.md 7b measures the D=128 kernel against.
+        try:
+            n = 16384
+            pool = pools[n][:2]
+
+            def lib_sdpa(q, k, v, _mask, causal):
+                return torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
+
+            ms = time_variant(lib_sdpa, pool, False, iters=10)
+            extras["library_reference_point_torch_sdpa_f16_n16384"] = {
+                "ms": round(ms, 5), "tflops": round(flops(1, H, n, D) / (ms * 1e-3) / 1e12, 2),
+                "note": "torch.nn.functional.scaled_dot_product_attention (cuDNN / flash backend), for context"}
+        except Exception as exc:  # noqa: BLE001 - a missing backend must not fail the bench
+            extras["library_reference_point_torch_sdpa_f16_n16384"] = {"error": repr(exc)[:200]}
         line["config"]["extra_sweeps"] = extras
         del pools
         torch.cuda.empty_cache()
