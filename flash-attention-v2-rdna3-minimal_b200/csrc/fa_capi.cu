@@ -183,6 +183,11 @@ int choose_kernel_shape(const Problem& p) {
   if (!tc) return FA_KERNEL_SIMT;
   if (p.D > 128) return FA_KERNEL_WIDE;  // two Q tiles no longer fit in TMEM: one tile, two S buffers
   if (p.Nq <= fa::kTileM) return FA_KERNEL_TC1;
+  const long long tiles128 = static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM);
+  // Head dims <= 64, non-causal: tensor memory has 128 spare columns there, so P gets its own region and
+  // S_t(j+1) is issued while softmax_t(j) still runs (fa_fwd_ws3.cuh) - the S -> P -> PV -> S chain loses its
+  // tensor-core tail.  Measured fp16 H=16 D=64: 841 vs 721 TFLOPS at N=16384, 640 vs 572 at N=4096.
+  if (!p.causal && p.D <= 64 && tiles128 > 148) return FA_KERNEL_WS3;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   // Causal with fewer than two 256-row blocks per SM: the one-tile arrangement halves the scheduling
   // grain, which matters more than its extra K/V traffic while the triangle leaves SMs idle (measured

@@ -18,6 +18,10 @@
 // Without the tensor-core wait nothing staggers the two softmax groups either.  Kept as FA_KERNEL_WS3
 // (selectable, never chosen automatically) with these numbers.
 //
+// HEAD DIM 64 is different: S0 S1 O0 O1 take 384 columns there, which leaves room for a P region per tile that
+// does not alias S.  The same protocol then needs neither shared memory nor proxy fences (tcgen05.st + TS product
+// as in ws / ws2), and the early S issue is free - see the result line in DESIGN.md 3.6.
+//
 // Protocol changes against ws2:
 //   - softmax warps signal "S_t(j) has been read" (after the lazy-rescale decision, which may re-read S) on a
 //     leader barrier; the leader then issues S_t(j+1) at once, BEFORE PV_t(j)
@@ -34,7 +38,8 @@ struct Ws3StepArgs {
   uint32_t bar_early, bar_mid, bar_late;  // P hand-off barriers (shared::cluster addresses in the leader)
   uint32_t bar_s_read;                    // "S_t(j) has been read" (shared::cluster address in the leader)
   uint32_t bar_pv_done;                   // this CTA's "PV_t(j) done" barrier
-  uint8_t* p_row;                         // my 128-byte row inside the P block of my half
+  uint8_t* p_row;                         // my 128-byte row inside the P block of my half (shared-memory P)
+  uint32_t tP;                            // kDP = 64: TMEM address of my 32 P columns (P in spare tensor memory)
   int swz;                                // row & 7: the 128-byte swizzle XOR of my row
 };
 
@@ -134,12 +139,37 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
   // ---- the P tile is free once PV_t(j-1) has read it
   if (j > 0) mbar_wait(a.bar_pv_done, (j - 1) & 1, 45);
 
-  // ---- first 32 keys of my half -> shared memory -> "early" hand-off
+  // At head dim 64 tensor memory has 128 spare columns (S0 S1 O0 O1 take 384), enough for a P region per tile
+  // that does not alias S: P goes there with tcgen05.st and feeds a TS product - no fences, no shared memory.
+  constexpr bool kPTmem = (kDP == 64);
+  // columns [16 lo, 16 lo + 16 n) of my half, i.e. keys [32 lo ..): n = 2 (32 keys) or 1 (16 keys)
+  auto hand_off = [&](int key0, int nkeys, uint32_t bar) {
+    if constexpr (kPTmem) {
+      uint32_t pk[16];
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) store_chunk(ch);
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(a.bar_early);
+      for (int i = 0; i < 16; ++i) pk[i] = (2 * i < nkeys) ? pack2<kBF16>(s[key0 + 2 * i], s[key0 + 2 * i + 1]) : 0u;
+      if (nkeys == 32) {
+        tmem_st_x16(a.tP + key0 / 2, pk);
+      } else {
+        uint32_t lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) lo[e] = pk[e];
+        tmem_st_x8(a.tP + key0 / 2, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        if (ch < nkeys / 8) store_chunk(key0 / 8 + ch);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(bar);
+  };
+
+  // ---- first 32 keys of my half -> "early" hand-off
+  hand_off(0, 32, a.bar_early);
 
   // ---- second half, with the row sum of the first half in the MUFU shadow; "mid" and "late" hand-offs
   float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
@@ -148,19 +178,9 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
     exp4(i, nmc);
     fadd2(sum0, sum1, sum0, sum1, s[i - 32], s[i - 31]);
     fadd2(sum2, sum3, sum2, sum3, s[i - 30], s[i - 29]);
-    if (i == 44) {  // keys [32,48) of my half
-      store_chunk(4);
-      store_chunk(5);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a.bar_mid);
-    }
+    if (i == 44) hand_off(32, 16, a.bar_mid);  // keys [32,48) of my half
   }
-  store_chunk(6);
-  store_chunk(7);
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(a.bar_late);
+  hand_off(48, 16, a.bar_late);
 #pragma unroll
   for (int i = 32; i < 64; i += 4) {
     fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
@@ -203,6 +223,8 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kOHalf = kDP / 2;
   auto col_s = [](int t) -> uint32_t { return static_cast<uint32_t>(t) * 128u; };
   auto col_o = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u; };
+  // head dim 64 only: O_t uses columns [256 + 128 t, +64); the 64 columns after it hold P_t (2 halves x 32)
+  auto col_p = [](int t) -> uint32_t { return 320u + static_cast<uint32_t>(t) * 128u; };
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -339,8 +361,13 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // k-step ks covers keys [16 ks, 16 ks + 16): P columns 16 ks.. of the K-major P tile (block ks / 4),
         // V rows 16 ks of the MN-major half tile
         auto pv_step = [&](int t, uint32_t p_lo, uint32_t v_lo, int ks, uint32_t acc) {
-          umma_ss2_2cta(tmem + col_o(t), p_lo + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), desc_hi,
-                        v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
+          if constexpr (kDP == 64) {  // P in spare tensor memory: half ks / 4 at columns col_p(t) + 32 (ks/4) + 8 (ks%4)
+            umma_ts2_2cta(tmem + col_o(t), tmem + col_p(t) + (ks >> 2) * 32 + (ks & 3) * 8,
+                          v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
+          } else {
+            umma_ss2_2cta(tmem + col_o(t), p_lo + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), desc_hi,
+                          v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
+          }
         };
         auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j for both CTAs
           const uint32_t v_lo = smem_desc_lo(sKV + (idx_v(j) % kS) * C::kSlotBytes, 16384);
@@ -417,6 +444,7 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
     a.bar_pv_done = bar_pv_done(t);
     a.p_row = smem + C::kP + t * C::kPBytes + half * 16384 + r * 128;  // my 128-byte row of the P block of my half
     a.swz = r & 7;
+    a.tP = tmem + lane_base + col_p(t) + half * 32;
 
     float m_run = -INFINITY;
     float l_run = 0.f;

@@ -59,6 +59,9 @@ def _st(B, H, N, D):
         ((1, 2, 300, 300, 256), _capi.FA_KERNEL_WIDE),        # head dim 129..256: one Q tile, two S buffers
         ((1, 16, 4096, 4096, 160), _capi.FA_KERNEL_WIDE),     # bench_with_sdpa.py:259-261 sweep point D = 16 * 10
         ((1, 2, 300, 300, 264), _capi.FA_KERNEL_SIMT),        # head dim > 256
+        ((2, 10, 4096, 4096, 64), _capi.FA_KERNEL_WS3),       # SDXL-like head dim 64: P in spare TMEM, early S issue
+        ((1, 16, 16384, 16384, 40), _capi.FA_KERNEL_WS3),
+        ((1, 8, 1024, 1024, 64), _capi.FA_KERNEL_WIDE),       # 64 tiles: one round of one-tile CTAs still wins
         ((2, 4, 77, 300, 40), _capi.FA_KERNEL_TC1),
     ],
 )
