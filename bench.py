@@ -568,17 +568,17 @@ def main():
             ms = time_variant(lambda *a: bfn(), [(None, None, None)] * 2, False, iters=8)
             bwd[str(n)] = {"ms": round(ms, 5), "tflops": round(2.5 * flops(1, H, n, D) / (ms * 1e-3) / 1e12, 2)}
         extras["f16_backward_noncausal"] = bwd
-        # head dims above 128 (the reference's head-dim sweep, bench_with_sdpa.py:259-261):
-        # fa_fwd_wide_kernel, one Q tile per CTA with the score tile double-buffered
+        # other head dims (the reference's head-dim sweep, bench_with_sdpa.py:259-261): above 128
+        # fa_fwd_wide / wide2 (one Q tile per CTA, score tile double-buffered, CTA pairs above 192)
         wide = {}
-        for d_head in (160, 192, 256):
+        for d_head in (64, 160, 192, 256):  # 64: the SDXL head dim (fa_fwd_ws3_kernel: P in spare TMEM columns)
             n = 16384
             pool = [tuple(torch.rand((1, H, n, d_head), dtype=dtype, device=dev) for _ in range(3)) for _ in range(2)]
             ms = time_variant(fa, pool, False, iters=10)
             wide[str(d_head)] = {"n": n, "ms": round(ms, 5),
                                  "tflops": round(flops(1, H, n, d_head) / (ms * 1e-3) / 1e12, 2)}
             del pool
-        extras["f16_noncausal_head_dims_above_128"] = wide
+        extras["f16_noncausal_other_head_dims"] = wide
         # context only, NOT this repo's code: the library kernel torch dispatches to for the same call on this box
         # (cuDNN fused attention at head dim 128).  It is the bar DESIGN.md 7b measures the D=128 kernel against.
         try:
