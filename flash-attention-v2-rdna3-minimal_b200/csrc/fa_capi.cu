@@ -187,7 +187,9 @@ int choose_kernel_shape(const Problem& p) {
   // Head dims <= 64, non-causal: tensor memory has 128 spare columns there, so P gets its own region and
   // S_t(j+1) is issued while softmax_t(j) still runs (fa_fwd_ws3.cuh) - the S -> P -> PV -> S chain loses its
   // tensor-core tail.  Measured fp16 H=16 D=64: 841 vs 721 TFLOPS at N=16384, 640 vs 572 at N=4096.
-  if (!p.causal && p.D <= 64 && tiles128 > 148) return FA_KERNEL_WS3;
+  // (Not for short KV loops - cross-attention with Nkv = 77 is one tile: the pair's cluster start-up then costs
+  // more than it saves, 21.0 vs 17.7 us at B=2 H=10 Nq=4096 D=64, tools/bench_sd_shapes.py.)
+  if (!p.causal && p.D <= 64 && tiles128 > 148 && p.Nkv >= 4 * fa::kTileN) return FA_KERNEL_WS3;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   // Causal with fewer than two 256-row blocks per SM: the one-tile arrangement halves the scheduling
   // grain, which matters more than its extra K/V traffic while the triangle leaves SMs idle (measured
@@ -369,6 +371,7 @@ bool sk_eligible(const Problem& p, int n_sm) {
   // N=16384 (6.92 -> 7: 1.2 %), 1185 vs 1214 at N=4096 (1.73 -> 2, but too few KV tiles per CTA to
   // amortise the two extra unit boundaries).
   if (units < 2LL * n_sm) return false;
+  if (p.Nkv < 4 * fa::kTileN) return false;  // units of a tile or two: nothing to split, only boundaries to pay for
   const long long rounds = (units + n_sm - 1) / n_sm;
   return rounds * n_sm * 100 >= units * 105;
 }

@@ -61,6 +61,7 @@ def _st(B, H, N, D):
         ((1, 2, 300, 300, 264), _capi.FA_KERNEL_SIMT),        # head dim > 256
         ((2, 10, 4096, 4096, 64), _capi.FA_KERNEL_WS3),       # SDXL-like head dim 64: P in spare TMEM, early S issue
         ((1, 16, 16384, 16384, 40), _capi.FA_KERNEL_WS3),
+        ((2, 10, 4096, 77, 64), _capi.FA_KERNEL_WS),          # SDXL cross-attention: one KV tile, the pair start-up does not pay
         ((1, 8, 1024, 1024, 64), _capi.FA_KERNEL_WIDE),       # 64 tiles: one round of one-tile CTAs still wins
         ((2, 4, 77, 300, 40), _capi.FA_KERNEL_TC1),
     ],
