@@ -59,16 +59,19 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
     for (int i = 0; i < 64; ++i)
       if (i >= lim) s[i] = -INFINITY;
   }
+  // Share of the exponentials on the FMA pipes.  At head dim 64 the softmax groups no longer wait for the tensor
+  // cores, so the MUFU is the binding pipe and a larger share pays: 2 of 8 pairs 870 TFLOPS, 1 843, 3 833, 4 770.
+  constexpr int kEmu = (kDP == 64) ? 2 : kEmuPairs;
   auto exp4 = [&](int i, float nmc_) {
     ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc_, nmc_);
     ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc_, nmc_);
-    if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
+    if ((((i >> 1) * kEmu) & 7) < kEmu) {
       ex2_fma2(s[i], s[i + 1]);
     } else {
       s[i] = ex2_approx(s[i]);
       s[i + 1] = ex2_approx(s[i + 1]);
     }
-    if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
+    if (((((i >> 1) + 1) * kEmu) & 7) < kEmu) {
       ex2_fma2(s[i + 2], s[i + 3]);
     } else {
       s[i + 2] = ex2_approx(s[i + 2]);
