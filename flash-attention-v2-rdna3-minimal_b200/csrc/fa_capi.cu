@@ -189,7 +189,11 @@ int choose_kernel_shape(const Problem& p) {
   // tensor-core tail.  Measured fp16 H=16 D=64: 841 vs 721 TFLOPS at N=16384, 640 vs 572 at N=4096.
   // (Not for short KV loops - cross-attention with Nkv = 77 is one tile: the pair's cluster start-up then costs
   // more than it saves, 21.0 vs 17.7 us at B=2 H=10 Nq=4096 D=64, tools/bench_sd_shapes.py.)
-  if (!p.causal && p.D <= 64 && tiles128 > 148 && p.Nkv >= 4 * fa::kTileN) return FA_KERNEL_WS3;
+  // Causal too (the four Q tiles of a pair run in lock step over the tiles the last one needs): 688 vs 619 TFLOPS
+  // at N=16384; small causal problems keep the 128-row grain of the one-tile kernel (415 vs 373 at N=4096).
+  const long long blocks256 = static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM));
+  if (p.D <= 64 && tiles128 > 148 && p.Nkv >= 4 * fa::kTileN && (!p.causal || blocks256 >= 2 * 148))
+    return FA_KERNEL_WS3;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   // Causal with fewer than two 256-row blocks per SM: the one-tile arrangement halves the scheduling
   // grain, which matters more than its extra K/V traffic while the triangle leaves SMs idle (measured
@@ -476,10 +480,10 @@ int launch_ws2(const Plan& pl, float* lse, cudaStream_t stream) {
 }
 
 // two-tile kernel on CTA pairs with P through shared memory (S_t(j+1) issued ahead of PV_t(j)): non-causal
-template <int kDP, bool kBF16>
+template <int kDP, bool kBF16, bool kCausal>
 int launch_ws3(const Plan& pl, float* lse, cudaStream_t stream) {
   const Problem& p = pl.p;
-  auto kernel = fa::fa_fwd_ws3_kernel<kDP, kBF16>;
+  auto kernel = fa::fa_fwd_ws3_kernel<kDP, kBF16, kCausal>;
   constexpr int smem = fa::Ws3Cfg<kDP>::kTotal;
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
@@ -524,9 +528,7 @@ int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t strea
     }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_QUAD2: return launch_quad2<kDP, kBF16, kCausal>(pl, lse, stream);
-    case FA_KERNEL_WS3:
-      if constexpr (!kCausal) return launch_ws3<kDP, kBF16>(pl, lse, stream);
-      return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // non-causal only
+    case FA_KERNEL_WS3: return launch_ws3<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_WS2:
       if constexpr (!kCausal) return launch_ws2<kDP, kBF16>(pl, lse, stream);
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // the pair kernel is non-causal only

@@ -1,5 +1,5 @@
 // "ws3": the two-tile kernel on CTA pairs (fa_fwd_ws2.cuh) with P routed through SHARED memory so that
-// S_t(j+1) no longer has to wait for O_t += P_t(j) V.  Non-causal, head dim 128 (padded) or 64.
+// S_t(j+1) no longer has to wait for O_t += P_t(j) V.  Head dim 128 (padded) or 64.
 //
 // In fa_fwd_ws.cuh / fa_fwd_ws2.cuh P (16 bit) overwrites the S columns in tensor memory, so the next score
 // tile of a Q tile can only be issued after the PV product that reads P - the tail of the S -> softmax -> P ->
@@ -45,16 +45,20 @@ struct Ws3StepArgs {
 
 // One softmax step of one thread, P through shared memory (see the header; the arithmetic is that of
 // ws_softmax_step in fa_fwd_ws.cuh, non-causal).
+//   causal_tile / lim_c   this tile needs the causal mask: columns i >= lim_c of my half are hidden (lim_c <= 0:
+//                         the whole half - the lock-step extra tiles of the earlier Q tiles of a pair)
 template <int kDP, bool kBF16>
 __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int lane, int col0,
                                                  int Nkv, float c, float& m_run, float& l_run, int j,
                                                  float* my_max, const float* other_max, int pair_bar,
-                                                 const Ws3StepArgs& a) {
+                                                 const Ws3StepArgs& a, bool causal_tile = false, int lim_c = 64) {
   constexpr int kOHalf = kDP / 2;
   const bool tail = (col0 + 64 > Nkv);
+  const bool masked = tail || causal_tile;
   int lim = 64;
-  if (tail) {
-    lim = Nkv - col0;
+  if (masked) {
+    const int valid = tail ? (Nkv - col0) : 64;
+    lim = causal_tile ? min(valid, lim_c) : valid;
 #pragma unroll
     for (int i = 0; i < 64; ++i)
       if (i >= lim) s[i] = -INFINITY;
@@ -127,7 +131,7 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
     nmc = -m_run * c;
     tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));  // S is still intact in tensor memory
     tmem_wait_ld();
-    if (tail) {
+    if (masked) {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i >= lim) s[i] = -INFINITY;
@@ -213,7 +217,7 @@ struct Ws3Cfg {
   static_assert(kKHalfBytes <= kSlotBytes && kVHalfBytes <= kSlotBytes && kTotal <= 232448, "shared memory budget");
 };
 
-template <int kDP, bool kBF16>
+template <int kDP, bool kBF16, bool kCausal>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWsThreads, 1)
 fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_k64,  // box {64 head-dim columns, 64 keys}
@@ -257,11 +261,18 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int blk = blockIdx.x;  // 256-row query block; the pair is blocks (2p, 2p+1), grid padded to even
+  // 256-row query block; the pair is blocks (2p, 2p+1), grid padded to even; causal: longest pairs first
+  const int pair = kCausal ? (static_cast<int>(gridDim.x / 2) - 1 - static_cast<int>(blockIdx.x / 2))
+                           : static_cast<int>(blockIdx.x / 2);
+  const int blk = 2 * pair + static_cast<int>(rank);
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int row0 = blk * 2 * kTileM;
-  const int n = (p.Nkv + kTileN - 1) / kTileN;  // KV tiles: the same for all four Q tiles of the pair
+  // KV tiles: the four Q tiles of the pair advance in lock step, so under a causal mask all visit the tiles the LAST
+  // one needs (4 pair + 4); the extra tiles are fully masked for the earlier ones (P = 0, nothing is added)
+  int n_ = (p.Nkv + kTileN - 1) / kTileN;
+  if (kCausal) n_ = min(n_, 4 * pair + 4);
+  const int n = n_;
   auto idx_k = [](int j) { return j == 0 ? 0 : 2 * j - 1; };  // ring (= consumption) order K0 K1 V0 K2 V1 ...
   auto idx_v = [n](int j) { return (j + 1 < n) ? 2 * j + 2 : 2 * j + 1; };
 
@@ -460,8 +471,10 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
+      const int g = 2 * blk + t;  // my Q tile's index: KV tile j >= g needs the causal mask
       ws3_softmax_step<kDP, kBF16>(s, tS, tO, lane, j * kTileN + half * 64, p.Nkv, c, m_run, l_run, j,
-                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar, a);
+                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar, a,
+                                   kCausal && j >= g, r - (j - g) * kTileN + 1 - half * 64);
     }
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (the tile's Q buffer) -> TMA store

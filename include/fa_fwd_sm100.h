@@ -63,8 +63,8 @@ extern "C" {
                                   (16 softmax warps on the one tile); head dims <= 128 */
 #define FA_KERNEL_WS3 9        /* FA_KERNEL_WS2 with P outside the S columns, so that S_t(j+1) is issued ahead of
                                   O_t += P_t(j) V: in spare tensor memory at head dims <= 64 (the default there for
-                                  non-causal problems), through shared memory at head dim 128 (measured slower, never
-                                  automatic); non-causal (causal requests run FA_KERNEL_WS) */
+                                  all but small or short-KV problems), through shared memory at head dim 128 (measured
+                                  slower, never automatic) */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu

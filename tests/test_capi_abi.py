@@ -73,6 +73,13 @@ def test_kernel_selection_is_pure_host_logic(shape, expected):
     assert k == expected
 
 
+def test_kernel_selection_causal_head_dim_64():
+    st = _st(1, 16, 16384, 64)
+    assert _capi.select_kernel(1, 16, 16384, 16384, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WS3
+    st = _st(1, 16, 4096, 64)  # 256 blocks < 2 per SM: the one-tile kernel's 128-row grain
+    assert _capi.select_kernel(1, 16, 4096, 4096, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WIDE
+
+
 @pytest.mark.parametrize(
     "n,expected",
     [
