@@ -38,9 +38,18 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC or put /usr/local/cuda/bin on PATH)")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def source_files() -> list[str]:
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     files.append(os.path.join(INCLUDE, "fa_fwd_sm100.h"))
+    files.append(os.path.join(INCLUDE, "fa_fwd_sm100_test.h"))
     return files
 
 

@@ -23,8 +23,8 @@
 #include <vector>
 
 #include "../../include/fa_fwd_sm100.h"
+#include "../../include/fa_fwd_sm100_test.h"
 #include "fa_bwd_tc.cuh"
-#include "fa_bwd_ws.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
@@ -32,7 +32,6 @@
 #include "fa_fwd_wide.cuh"
 #include "fa_fwd_wide2.cuh"
 #include "fa_fwd_ws2.cuh"
-#include "fa_fwd_quad2.cuh"
 #include "fa_fwd_ws3.cuh"
 #include "umma_probe.cuh"
 #include "umma2_probe.cuh"
@@ -43,7 +42,8 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_forced_kernel{FA_KERNEL_AUTO};
 std::atomic<int> g_wide_pairs{1};  // head dims 193..256: CTA-pair kernel (fa_set_wide_pairs)
-std::atomic<int> g_bwd_kernel{FA_BWD_KERNEL_TC1};  // measured faster than WS (tools/bench_bwd.py)
+// programmatic dependent launch for the forward kernels (fa_set_pdl / FA_NO_PDL=1 switch it off for A/B runs)
+std::atomic<int> g_pdl{std::getenv("FA_NO_PDL") == nullptr ? 1 : 0};
 #ifdef FA_TRACE
 unsigned long long* g_trace = nullptr;  // debug builds only (tools/trace_ws.py)
 #define FA_TP_TRACE , g_trace
@@ -289,6 +289,29 @@ int set_smem(K kernel, int bytes, std::atomic<uint64_t>* done = nullptr, int dev
   return FA_OK;
 }
 
+// One launch of a forward kernel.  With PDL the launch carries the programmatic-stream-serialization
+// attribute: the kernel may become resident while its predecessor on the stream is still running and does
+// its prologue (barrier init, TMEM allocation, descriptor / L2 prefetch) there; every kernel calls
+// griddepcontrol.wait before it touches global memory, so stream order is preserved for the data.
+// Cluster kernels carry their cluster shape at compile time (__cluster_dims__).
+template <typename... KArgs, typename... Args>
+int launch_fwd(void (*kernel)(KArgs...), dim3 grid, int threads, int smem, cudaStream_t stream,
+               Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  FA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
 template <int kDP, bool kBF16, bool kCausal>
 int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   const Problem& p = pl.p;
@@ -299,25 +322,27 @@ int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
-  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, fa::kWsThreads, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
 // ---------------------------------------------------------------------------------------------
 // persistent stream-K forward: per-(device, stream) workspace for the partial results of split units
 // ---------------------------------------------------------------------------------------------
+// One entry per (device, stream), always sized for the largest configuration (SM count + 1 slots of the
+// head-dim-128 slot size, ~20 MB), so an entry is never re-allocated and its address - which CUDA graphs
+// captured on that stream have baked in - stays valid until fa_host_workspace_release().  Launches on one
+// stream are ordered, so one slot set per stream is enough; see include/fa_fwd_sm100.h for the rule this
+// implies for graphs replayed on other streams.
 struct SkWorkspace {
   int device = -1;
   cudaStream_t stream = nullptr;
   float* ws = nullptr;
   int* flags = nullptr;
-  size_t ws_bytes = 0;
-  int flag_count = 0;
+  int slots = 0;
 };
 std::mutex g_sk_mu;
 std::vector<SkWorkspace> g_sk_ws;
+constexpr size_t kSkMaxWorkspaces = 64;
 
 int sm_count(int device) {
   static std::mutex mu;
@@ -333,64 +358,93 @@ int sm_count(int device) {
   return n;
 }
 
-// Workspace for launches on `stream`, or nullptr if none can be provided right now (stream capture
-// in progress with nothing cached, allocation failure, too many streams): the caller then uses the
-// one-shot kernel.  Launches on one stream are ordered, so one slot set per stream is enough.
-SkWorkspace* get_sk_workspace(int device, cudaStream_t stream, size_t ws_bytes, int flag_count) {
+// Workspace for launches on `stream`, or nullptr if none can be provided right now (stream capture in
+// progress with nothing cached, allocation failure, more than kSkMaxWorkspaces streams): the caller then
+// uses the one-shot kernel.
+SkWorkspace* get_sk_workspace(int device, cudaStream_t stream, int slots) {
   std::lock_guard<std::mutex> lk(g_sk_mu);
   for (auto& w : g_sk_ws)
-    if (w.device == device && w.stream == stream && w.ws_bytes >= ws_bytes && w.flag_count >= flag_count)
-      return &w;
+    if (w.device == device && w.stream == stream && w.slots >= slots) return &w;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
     (void)cudaGetLastError();
     return nullptr;
   }
-  if (g_sk_ws.size() >= 16) return nullptr;
+  if (g_sk_ws.size() >= kSkMaxWorkspaces) return nullptr;
   SkWorkspace w;
   w.device = device;
   w.stream = stream;
+  w.slots = slots;
+  const size_t ws_bytes = static_cast<size_t>(slots) * fa::kSkSlotFloatsMax * sizeof(float);
+  const size_t flag_bytes = static_cast<size_t>(slots) * 2 * sizeof(int);
+  // The flags are cleared ON THE LAUNCH STREAM (verified above not to be capturing): the first kernel that
+  // reads them is ordered behind the memset whatever kind of stream this is.
   if (cudaMalloc(reinterpret_cast<void**>(&w.ws), ws_bytes) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&w.flags), flag_count * sizeof(int)) != cudaSuccess ||
-      cudaMemset(w.flags, 0, flag_count * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(reinterpret_cast<void**>(&w.flags), flag_bytes) != cudaSuccess ||
+      cudaMemsetAsync(w.flags, 0, flag_bytes, stream) != cudaSuccess) {
     (void)cudaGetLastError();
     if (w.ws) cudaFree(w.ws);
     if (w.flags) cudaFree(w.flags);
     return nullptr;
   }
-  w.ws_bytes = ws_bytes;
-  w.flag_count = flag_count;
-  g_sk_ws.reserve(16);  // pointers handed out stay valid
+  g_sk_ws.reserve(kSkMaxWorkspaces);  // pointers handed out stay valid
   g_sk_ws.push_back(w);
   return &g_sk_ws.back();
 }
 
+void release_sk_workspaces(int device) {
+  std::lock_guard<std::mutex> lk(g_sk_mu);
+  for (size_t i = 0; i < g_sk_ws.size();) {
+    if (g_sk_ws[i].device == device) {
+      cudaFree(g_sk_ws[i].ws);
+      cudaFree(g_sk_ws[i].flags);
+      g_sk_ws[i] = g_sk_ws.back();
+      g_sk_ws.pop_back();
+    } else {
+      ++i;
+    }
+  }
+}
+
+// What the persistent kernel can run at all: non-causal, whole 256-row query blocks.
+bool sk_possible(const Problem& p) { return !p.causal && p.Nq % (2 * fa::kTileM) == 0; }
+
+// Cost model for head dims <= 128, in units of one "step" = the time the two-tile
+// kernels need for one KV tile of a 256-row query block (~1.9 us at the sustained clock):
+//   one-shot, two tiles per CTA (ws)   rounds of U CTAs on n_sm SMs, each T steps + a fixed cost per CTA
+//   persistent (sk)                    ceil(U T / n_sm) steps + a cost per unit boundary + the fixed cost once
+//   one tile per CTA (wide)            rounds of U128 CTAs, each T shorter steps + a (smaller) fixed cost
+// The constants are fitted to the round-2 A/B runs (tools/ab_bench.py, profiles/r02_ab_*.json).
+struct KernelCosts {
+  double ws, sk, wide;
+};
+KernelCosts estimate_costs(const Problem& p, int n_sm) {
+  const double T = static_cast<double>((p.Nkv + fa::kTileN - 1) / fa::kTileN) * (p.causal ? 0.5 : 1.0);
+  const long long U = static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM));
+  const long long U128 = static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM);
+  KernelCosts k;
+  k.ws = static_cast<double>((U + n_sm - 1) / n_sm) * (T + 2.6);
+  const double per_cta = std::ceil(static_cast<double>(U) * T / n_sm);
+  k.sk = per_cta + 0.8 * (std::ceil(per_cta / T) + 1.0) + 2.6;
+  k.wide = static_cast<double>((U128 + n_sm - 1) / n_sm) * (0.72 * T + 2.2);
+  return k;
+}
+
 // shape-only eligibility (the SM count defaults to a B200's 148 when no device is consulted)
 bool sk_eligible(const Problem& p, int n_sm) {
-  if (p.causal || p.Nq % (2 * fa::kTileM) != 0 || n_sm <= 0) return false;
-  const long long units = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
-  // Correct from one unit per SM (a CTA range then spans at least one whole unit).  It pays where the
-  // one-shot kernel loses more than ~5 % to whole rounds: measured on B200 (tools/ab_bench.py, fp16
-  // B=1 H=16 D=128) 1371 vs 1298 TFLOPS at N=8192 (3.46 rounds -> 4: 15.6 % lost), 1434 vs 1437 at
-  // N=16384 (6.92 -> 7: 1.2 %), 1185 vs 1214 at N=4096 (1.73 -> 2, but too few KV tiles per CTA to
-  // amortise the two extra unit boundaries).
-  if (units < 2LL * n_sm) return false;
+  if (!sk_possible(p) || n_sm <= 0) return false;
   if (p.Nkv < 4 * fa::kTileN) return false;  // units of a tile or two: nothing to split, only boundaries to pay for
-  const long long rounds = (units + n_sm - 1) / n_sm;
-  return rounds * n_sm * 100 >= units * 105;
+  const KernelCosts k = estimate_costs(p, n_sm);
+  return k.sk < 0.97 * k.ws && k.sk < 0.97 * k.wide;
 }
 
 template <int kDP, bool kBF16>
 int launch_sk(const Plan& pl, float* lse, cudaStream_t stream, bool* launched) {
   const Problem& p = pl.p;
   *launched = false;
-  const int G = sm_count(pl.device);
-  const long long units = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
-  // an explicit FA_KERNEL_SK request runs from one unit per SM (tests exercise the split paths there)
-  const bool forced = g_forced_kernel.load() == FA_KERNEL_SK;
-  if (p.causal || p.Nq % (2 * fa::kTileM) != 0 || G <= 0 || units < (forced ? 1LL : 2LL) * G) return FA_OK;
-  const size_t ws_bytes = static_cast<size_t>(G + 1) * fa::SkSlot<kDP>::kFloats * sizeof(float);
-  SkWorkspace* w = get_sk_workspace(pl.device, stream, ws_bytes, 2 * (G + 1));
+  const int n_sm = sm_count(pl.device);
+  if (!sk_possible(p) || n_sm <= 0) return FA_OK;
+  SkWorkspace* w = get_sk_workspace(pl.device, stream, n_sm + 1);
   if (w == nullptr) return FA_OK;
   auto kernel = fa::fa_fwd_sk_kernel<kDP, kBF16>;
   constexpr int smem = fa::SkCfg<kDP>::kTotal;
@@ -400,31 +454,28 @@ int launch_sk(const Plan& pl, float* lse, cudaStream_t stream, bool* launched) {
   const int T = (p.Nkv + fa::kTileN - 1) / fa::kTileN;
   const int P = p.Nq / (2 * fa::kTileM);
   const long long U = static_cast<long long>(p.B) * p.H * P;
+  // one CTA per SM, fewer when there are fewer (unit, KV tile) items than SMs
+  const int G = static_cast<int>(std::min<long long>(n_sm, U * T));
   // all but the last full round are data-parallel; the last G + U % G units are split evenly
-  const int dp = (U % G == 0) ? static_cast<int>(U / G) : static_cast<int>(U / G) - 1;
+  const int dp = (U % G == 0) ? static_cast<int>(U / G) : static_cast<int>(std::max<long long>(U / G - 1, 0));
   const long long W = (U - static_cast<long long>(dp) * G) * T;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, w->ws, w->flags, W, dp, T, P FA_TP_TRACE};
-  kernel<<<G, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  *launched = true;
-  return FA_OK;
+  rc = launch_fwd(kernel, dim3(G), fa::kWsThreads, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
+  *launched = (rc == FA_OK);
+  return rc;
 }
 
-template <int kDP, bool kBF16, bool kCausal, bool kPsmem>
+template <int kDP, bool kBF16, bool kCausal>
 int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
   const Problem& p = pl.p;
-  auto kernel = fa::fa_fwd_tc1_kernel<kDP, kBF16, kCausal, kPsmem>;
+  auto kernel = fa::fa_fwd_tc1_kernel<kDP, kBF16, kCausal>;
   constexpr int smem = fa::Tc1Smem<kDP>::kTotal;
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
-  kernel<<<grid, 128, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, 128, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
 template <int kDP, bool kBF16, bool kCausal>
@@ -437,28 +488,7 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
-  kernel<<<grid, fa::kWideThreads, smem, stream>>>(pl.mq, pl.mk, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
-}
-
-// one-tile kernel on CTA pairs with four threads per query row: head dims <= 128
-template <int kDP, bool kBF16, bool kCausal>
-int launch_quad2(const Plan& pl, float* lse, cudaStream_t stream) {
-  const Problem& p = pl.p;
-  auto kernel = fa::fa_fwd_quad2_kernel<kDP, kBF16, kCausal>;
-  constexpr int smem = fa::Quad2Cfg<kDP>::kTotal;
-  static std::atomic<uint64_t> configured{0};
-  int rc = set_smem(kernel, smem, &configured, pl.device);
-  if (rc) return rc;
-  fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
-  const int tiles = (p.Nq + fa::kTileM - 1) / fa::kTileM;
-  dim3 grid((tiles + 1) & ~1, p.H, p.B);
-  kernel<<<grid, fa::kQuadThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, fa::kWideThreads, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
 // two-tile kernel on CTA pairs (cluster of 2, cta_group::2): non-causal, head dims <= 128
@@ -473,10 +503,7 @@ int launch_ws2(const Plan& pl, float* lse, cudaStream_t stream) {
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   const int blocks = (p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM);
   dim3 grid((blocks + 1) & ~1, p.H, p.B);  // whole pairs
-  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, fa::kWsThreads, smem, stream, pl.mq, pl.mk64, pl.mv, pl.mo, tp);
 }
 
 // two-tile kernel on CTA pairs with P through shared memory (S_t(j+1) issued ahead of PV_t(j)): non-causal
@@ -491,10 +518,7 @@ int launch_ws3(const Plan& pl, float* lse, cudaStream_t stream) {
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   const int blocks = (p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM);
   dim3 grid((blocks + 1) & ~1, p.H, p.B);
-  kernel<<<grid, fa::kWsThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, fa::kWsThreads, smem, stream, pl.mq, pl.mk64, pl.mv, pl.mo, tp);
 }
 
 // CTA-pair kernel (cluster of 2, cta_group::2): padded head dim 192 or 256
@@ -509,10 +533,7 @@ int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   const int tiles = (p.Nq + fa::kTileM - 1) / fa::kTileM;
   dim3 grid((tiles + 1) & ~1, p.H, p.B);  // whole pairs: an odd last tile gets a partner that is all padding
-  kernel<<<grid, fa::kWideThreads, smem, stream>>>(pl.mq, pl.mk64, pl.mv, pl.mo, tp);
-  FA_CUDA_TRY(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return FA_OK;
+  return launch_fwd(kernel, grid, fa::kWideThreads, smem, stream, pl.mq, pl.mk64, pl.mv, pl.mo, tp);
 }
 
 template <int kDP, bool kBF16, bool kCausal>
@@ -527,13 +548,15 @@ int launch_tc_variant(int kernel, const Plan& pl, float* lse, cudaStream_t strea
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // not eligible / no workspace
     }
     case FA_KERNEL_WS: return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
-    case FA_KERNEL_QUAD2: return launch_quad2<kDP, kBF16, kCausal>(pl, lse, stream);
-    case FA_KERNEL_WS3: return launch_ws3<kDP, kBF16, kCausal>(pl, lse, stream);
+    case FA_KERNEL_WS3:
+      // P outside the S columns needs spare tensor memory: head dims <= 64 (the shared-memory route at 128 was
+      // measured 5 % slower than ws2 and is no longer instantiated)
+      if constexpr (kDP == 64) return launch_ws3<kDP, kBF16, kCausal>(pl, lse, stream);
+      return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);
     case FA_KERNEL_WS2:
       if constexpr (!kCausal) return launch_ws2<kDP, kBF16>(pl, lse, stream);
       return launch_ws<kDP, kBF16, kCausal>(pl, lse, stream);  // the pair kernel is non-causal only
-    case FA_KERNEL_TC1: return launch_tc1<kDP, kBF16, kCausal, false>(pl, lse, stream);
-    case FA_KERNEL_TC1_PSMEM: return launch_tc1<kDP, kBF16, kCausal, true>(pl, lse, stream);
+    case FA_KERNEL_TC1: return launch_tc1<kDP, kBF16, kCausal>(pl, lse, stream);
   }
   return fail(FA_ERR_INVALID_ARG, "unknown tensor-core kernel selector");
 }
@@ -640,21 +663,12 @@ template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
                   cudaStream_t stream) {
   dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
-  if (g_bwd_kernel.load() == FA_BWD_KERNEL_TC1) {
-    auto kernel = fa::fa_bwd_tc_kernel<kDP, kBF16, kCausal>;
-    constexpr int smem = fa::BwdSmem<kDP>::kTotal;
-    static std::atomic<uint64_t> configured{0};
-    int rc = set_smem(kernel, smem, &configured, device);
-    if (rc) return rc;
-    kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
-  } else {
-    auto kernel = fa::fa_bwd_ws_kernel<kDP, kBF16, kCausal>;
-    constexpr int smem = fa::BwdWsSmem<kDP>::kTotal;
-    static std::atomic<uint64_t> configured{0};
-    int rc = set_smem(kernel, smem, &configured, device);
-    if (rc) return rc;
-    kernel<<<grid, fa::kBwdWsThreads, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
-  }
+  auto kernel = fa::fa_bwd_tc_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::BwdSmem<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, device);
+  if (rc) return rc;
+  kernel<<<grid, 256, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq, bp);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
@@ -677,6 +691,57 @@ int dispatch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int
   FA_BWD_DISPATCH(128);
 #undef FA_BWD_DISPATCH
 }
+
+// Tensor maps of one backward call, cached like the forward's Plan (encoding seven maps costs ~10 us of
+// host time per call; training loops present the same buffers again and again through the caching allocator).
+struct BwdPlan {
+  const void* ptr[7];
+  int B, H, Nq, Nkv, D, dtype, device;
+  int64_t st[6][4];
+  BwdMaps m;
+  uint64_t stamp;
+};
+struct BwdPlanCache {
+  std::mutex mu;
+  std::vector<BwdPlan> plans;
+  uint64_t clock = 0;
+  static constexpr size_t kCap = 64;
+  int get(const BwdPlan& key, BwdMaps* out) {
+    std::lock_guard<std::mutex> lk(mu);
+    ++clock;
+    for (auto& pl : plans) {
+      if (memcmp(pl.ptr, key.ptr, sizeof key.ptr) == 0 && pl.B == key.B && pl.H == key.H && pl.Nq == key.Nq &&
+          pl.Nkv == key.Nkv && pl.D == key.D && pl.dtype == key.dtype && pl.device == key.device &&
+          memcmp(pl.st, key.st, sizeof key.st) == 0) {
+        pl.stamp = clock;
+        *out = pl.m;
+        return FA_OK;
+      }
+    }
+    BwdPlan pl = key;
+    pl.stamp = clock;
+    int rc;
+    const int B = key.B, H = key.H, Nq = key.Nq, Nkv = key.Nkv, D = key.D, dt = key.dtype;
+    if ((rc = make_map(&pl.m.q, key.ptr[0], B, H, Nq, D, key.st[0], dt, fa::kTileM))) return rc;
+    if ((rc = make_map(&pl.m.k, key.ptr[1], B, H, Nkv, D, key.st[1], dt, fa::kTileN))) return rc;
+    if ((rc = make_map(&pl.m.v, key.ptr[2], B, H, Nkv, D, key.st[2], dt, fa::kTileN))) return rc;
+    if ((rc = make_map(&pl.m.d_o, key.ptr[3], B, H, Nq, D, key.st[3], dt, fa::kTileM))) return rc;
+    if ((rc = make_map(&pl.m.dk, key.ptr[4], B, H, Nkv, D, key.st[4], dt, fa::kTileN))) return rc;
+    if ((rc = make_map(&pl.m.dv, key.ptr[5], B, H, Nkv, D, key.st[5], dt, fa::kTileN))) return rc;
+    if ((rc = make_map_dq(&pl.m.dq, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D))) return rc;
+    if (plans.size() < kCap) {
+      plans.push_back(pl);
+    } else {
+      size_t victim = 0;
+      for (size_t i = 1; i < plans.size(); ++i)
+        if (plans[i].stamp < plans[victim].stamp) victim = i;
+      plans[victim] = pl;
+    }
+    *out = pl.m;
+    return FA_OK;
+  }
+};
+BwdPlanCache g_bwd_plans;
 
 int check_device(int* device_out) {
   int dev = -1;
@@ -778,24 +843,44 @@ std::vector<size_t> plan_host_chunks(size_t heads, int Nq, int Nkv, int D, int c
 // ---------------------------------------------------------------------------------------------
 // host-buffer path: per-device workspace + three streams
 // ---------------------------------------------------------------------------------------------
-struct HostWs {
-  bool init = false;
-  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+// Two staging sets per device, used alternately: the H2D copies of call i+1 may run under the tail (last
+// kernel + D2H) of call i, which is what fa_fwd_sm100_host_async() is for.
+struct HostSet {
   void *dq = nullptr, *dk = nullptr, *dv = nullptr, *dout = nullptr;
   float* dlse = nullptr;
   size_t cap_q = 0, cap_kv = 0, cap_lse = 0;
+  cudaEvent_t done = nullptr;  // recorded on s_out behind the last D2H of the call that used the set
+  bool used = false;
+};
+struct HostWs {
+  bool init = false;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  HostSet set[2];
+  uint64_t calls = 0;
   std::vector<cudaEvent_t> ev_in, ev_run;
   std::mutex mu;  // one host call at a time per device (the workspace and its streams are per device);
                   // calls on different devices - the multi-GPU shard driven from one process - run concurrently
 };
 HostWs g_ws[64];
 
+void host_drain(HostWs& w) {
+  if (w.s_in) cudaStreamSynchronize(w.s_in);
+  if (w.s_run) cudaStreamSynchronize(w.s_run);
+  if (w.s_out) cudaStreamSynchronize(w.s_out);
+  (void)cudaGetLastError();
+}
+
 int ws_release(HostWs& w) {
-  if (w.dq) cudaFree(w.dq);
-  if (w.dk) cudaFree(w.dk);
-  if (w.dv) cudaFree(w.dv);
-  if (w.dout) cudaFree(w.dout);
-  if (w.dlse) cudaFree(w.dlse);
+  host_drain(w);
+  for (HostSet& st : w.set) {
+    if (st.dq) cudaFree(st.dq);
+    if (st.dk) cudaFree(st.dk);
+    if (st.dv) cudaFree(st.dv);
+    if (st.dout) cudaFree(st.dout);
+    if (st.dlse) cudaFree(st.dlse);
+    if (st.done) cudaEventDestroy(st.done);
+    st = HostSet();
+  }
   for (auto e : w.ev_in) cudaEventDestroy(e);
   for (auto e : w.ev_run) cudaEventDestroy(e);
   if (w.s_in) cudaStreamDestroy(w.s_in);
@@ -803,11 +888,165 @@ int ws_release(HostWs& w) {
   if (w.s_out) cudaStreamDestroy(w.s_out);
   w.init = false;  // (not `w = HostWs()`: the mutex the caller holds lives in w)
   w.s_in = w.s_run = w.s_out = nullptr;
-  w.dq = w.dk = w.dv = w.dout = nullptr;
-  w.dlse = nullptr;
-  w.cap_q = w.cap_kv = w.cap_lse = 0;
+  w.calls = 0;
   w.ev_in.clear();
   w.ev_run.clear();
+  return FA_OK;
+}
+
+// Enqueue one host-buffer forward on the device's three streams (caller holds w.mu).  On return with
+// FA_OK the work is in flight; `o` (and `lse`) are complete once s_out has drained.
+int host_enqueue(HostWs& w, const void* q, const void* k, const void* v, void* o, float* lse, int B, int H,
+                 int Nq, int Nkv, int D, int dtype, int causal, float scale) {
+  int rc;
+  if (!w.init) {
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+    w.init = true;
+  }
+  const size_t heads = size_t(B) * H;
+  const size_t q_head = size_t(Nq) * D * 2, kv_head = size_t(Nkv) * D * 2;
+  const size_t bytes_q = heads * q_head, bytes_kv = heads * kv_head;
+  const size_t bytes_lse = heads * Nq * sizeof(float);
+  HostSet& st = w.set[w.calls & 1];
+  if (st.cap_q < bytes_q || st.cap_kv < bytes_kv || (lse != nullptr && st.cap_lse < bytes_lse)) {
+    host_drain(w);  // growing frees buffers that calls still in flight may be using
+    if (st.cap_q < bytes_q) {
+      if (st.dq) cudaFree(st.dq);
+      if (st.dout) cudaFree(st.dout);
+      st.dq = st.dout = nullptr; st.cap_q = 0;
+      FA_CUDA_TRY(cudaMalloc(&st.dq, bytes_q));
+      FA_CUDA_TRY(cudaMalloc(&st.dout, bytes_q));
+      st.cap_q = bytes_q;
+    }
+    if (st.cap_kv < bytes_kv) {
+      if (st.dk) cudaFree(st.dk);
+      if (st.dv) cudaFree(st.dv);
+      st.dk = st.dv = nullptr; st.cap_kv = 0;
+      FA_CUDA_TRY(cudaMalloc(&st.dk, bytes_kv));
+      FA_CUDA_TRY(cudaMalloc(&st.dv, bytes_kv));
+      st.cap_kv = bytes_kv;
+    }
+    if (lse != nullptr && st.cap_lse < bytes_lse) {
+      if (st.dlse) cudaFree(st.dlse);
+      st.dlse = nullptr; st.cap_lse = 0;
+      FA_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&st.dlse), bytes_lse));
+      st.cap_lse = bytes_lse;
+    }
+  }
+  if (st.done == nullptr) FA_CUDA_TRY(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  // the set's previous user (two calls ago) must have copied its result out before we overwrite the buffers
+  if (st.used) FA_CUDA_TRY(cudaStreamWaitEvent(w.s_in, st.done, 0));
+
+  // chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D]
+  const std::vector<size_t> chunk_heads = plan_host_chunks(heads, Nq, Nkv, D, causal);
+  const size_t n_chunks = chunk_heads.size();
+  while (w.ev_in.size() < n_chunks) {
+    cudaEvent_t e1, e2;
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    w.ev_in.push_back(e1);
+    w.ev_run.push_back(e2);
+  }
+
+  // FA_HOST_TIMING=1: print host enqueue time and the device timeline per call (diagnostic; synchronises)
+  static const bool timing = std::getenv("FA_HOST_TIMING") != nullptr;
+  static cudaEvent_t t_ev[2] = {nullptr, nullptr};
+  static std::vector<cudaEvent_t> t_chunk;
+  const auto t_cpu0 = std::chrono::steady_clock::now();
+  if (timing) {
+    if (t_ev[0] == nullptr) { cudaEventCreate(&t_ev[0]); cudaEventCreate(&t_ev[1]); }
+    cudaEventRecord(t_ev[0], w.s_in);
+  }
+  const char* hq = static_cast<const char*>(q);
+  const char* hk = static_cast<const char*>(k);
+  const char* hv = static_cast<const char*>(v);
+  char* ho = static_cast<char*>(o);
+  size_t h0 = 0;
+  for (size_t c = 0; c < n_chunks; h0 += chunk_heads[c], ++c) {
+    const size_t nh = chunk_heads[c];
+    char* dq = static_cast<char*>(st.dq) + h0 * q_head;
+    char* dk = static_cast<char*>(st.dk) + h0 * kv_head;
+    char* dv = static_cast<char*>(st.dv) + h0 * kv_head;
+    char* dout = static_cast<char*>(st.dout) + h0 * q_head;
+    FA_CUDA_TRY(cudaMemcpyAsync(dq, hq + h0 * q_head, nh * q_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(dk, hk + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(dv, hv + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
+    FA_CUDA_TRY(cudaEventRecord(w.ev_in[c], w.s_in));
+    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_run, w.ev_in[c], 0));
+    if (timing) {
+      while (t_chunk.size() < 4 * (c + 1)) { cudaEvent_t e; cudaEventCreate(&e); t_chunk.push_back(e); }
+      cudaEventRecord(t_chunk[4 * c + 0], w.s_in);
+      cudaEventRecord(t_chunk[4 * c + 1], w.s_run);
+    }
+    // the chunk is a [1, nh, N, D] problem
+    Problem p{};
+    p.B = 1; p.H = static_cast<int>(nh); p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype;
+    p.causal = causal; p.scale = scale;
+    const int64_t cqs[4] = {int64_t(nh) * Nq * D, int64_t(Nq) * D, D, 1};
+    const int64_t cks[4] = {int64_t(nh) * Nkv * D, int64_t(Nkv) * D, D, 1};
+    if ((rc = validate(p, cqs, cks, cks, cqs))) return rc;
+    float* dl = (lse != nullptr) ? st.dlse + h0 * Nq : nullptr;
+    if ((rc = run_device(dq, dk, dv, dout, dl, p, w.s_run))) return rc;
+    FA_CUDA_TRY(cudaEventRecord(w.ev_run[c], w.s_run));
+    if (timing) cudaEventRecord(t_chunk[4 * c + 2], w.s_run);
+    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_out, w.ev_run[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(ho + h0 * q_head, dout, nh * q_head, cudaMemcpyDeviceToHost, w.s_out));
+    if (lse != nullptr)
+      FA_CUDA_TRY(cudaMemcpyAsync(lse + h0 * Nq, dl, nh * Nq * sizeof(float),
+                                  cudaMemcpyDeviceToHost, w.s_out));
+    if (timing) cudaEventRecord(t_chunk[4 * c + 3], w.s_out);
+  }
+  FA_CUDA_TRY(cudaEventRecord(st.done, w.s_out));
+  st.used = true;
+  ++w.calls;
+  if (timing) {
+    const auto t_cpu1 = std::chrono::steady_clock::now();
+    cudaEventRecord(t_ev[1], w.s_out);
+    cudaStreamSynchronize(w.s_out);
+    const auto t_cpu2 = std::chrono::steady_clock::now();
+    float dev_ms = 0.f;
+    cudaEventElapsedTime(&dev_ms, t_ev[0], t_ev[1]);
+    fprintf(stderr, "[fa_fwd_sm100_host] N=%d chunks=%zu enqueue %.3f ms, device span %.3f ms, total %.3f ms\n",
+            Nq, n_chunks, std::chrono::duration<double, std::milli>(t_cpu1 - t_cpu0).count(), dev_ms,
+            std::chrono::duration<double, std::milli>(t_cpu2 - t_cpu0).count());
+    for (size_t c = 0; c < n_chunks; ++c) {
+      float t[4];
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], t_ev[0], t_chunk[4 * c + i]);
+      fprintf(stderr, "    chunk %zu: H2D done %.3f, kernel start %.3f, kernel done %.3f, D2H done %.3f\n", c,
+              t[0], t[1], t[2], t[3]);
+    }
+  }
+  return FA_OK;
+}
+
+int host_call(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Nq,
+              int Nkv, int D, int dtype, int causal, float scale, bool wait) {
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
+    return fail(FA_ERR_INVALID_ARG, "q, k, v and o must not be null");
+  Problem chk{};
+  chk.B = B; chk.H = H; chk.Nq = Nq; chk.Nkv = Nkv; chk.D = D; chk.dtype = dtype;
+  chk.causal = causal; chk.scale = scale;
+  const int64_t qs[4] = {int64_t(H) * Nq * D, int64_t(Nq) * D, D, 1};
+  const int64_t ks[4] = {int64_t(H) * Nkv * D, int64_t(Nkv) * D, D, 1};
+  int rc = validate(chk, qs, ks, ks, qs);
+  if (rc) return rc;
+  int dev;
+  if ((rc = check_device(&dev))) return rc;
+  if (dev >= 64) return fail(FA_ERR_UNSUPPORTED, "device ordinal >= 64");
+  HostWs& w = g_ws[dev];
+  std::lock_guard<std::mutex> lk(w.mu);
+  rc = host_enqueue(w, q, k, v, o, lse, B, H, Nq, Nkv, D, dtype, causal, scale);
+  if (rc) {
+    // copies already enqueued still read and write the caller's buffers: drain before reporting the error,
+    // and never leave half a call behind for the next one
+    const std::string keep = g_err;
+    host_drain(w);
+    g_err = keep;
+    return rc;
+  }
+  if (wait) FA_CUDA_TRY(cudaStreamSynchronize(w.s_out));
   return FA_OK;
 }
 
@@ -829,7 +1068,7 @@ const char* fa_last_error(void) { return g_err.c_str(); }
 uint64_t fa_launch_count(void) { return g_launches.load(); }
 
 int fa_set_kernel(int kernel) {
-  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS3) return -FA_ERR_INVALID_ARG;
+  if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS3 || kernel == 3 || kernel == 8) return -FA_ERR_INVALID_ARG;
   return g_forced_kernel.exchange(kernel);
 }
 
@@ -843,10 +1082,7 @@ int fa_host_plan_chunks(int B, int H, int Nq, int Nkv, int D, int causal, int* o
 
 int fa_set_wide_pairs(int enable) { return g_wide_pairs.exchange(enable ? 1 : 0); }
 
-int fa_set_bwd_kernel(int kernel) {
-  if (kernel != FA_BWD_KERNEL_TC1 && kernel != FA_BWD_KERNEL_WS) return -FA_ERR_INVALID_ARG;
-  return g_bwd_kernel.exchange(kernel);
-}
+int fa_set_pdl(int enable) { return g_pdl.exchange(enable ? 1 : 0); }
 
 int fa_select_kernel(int B, int H, int Nq, int Nkv, int D, const int64_t q_strides[4],
                      const int64_t k_strides[4], const int64_t v_strides[4],
@@ -877,130 +1113,22 @@ int fa_fwd_sm100(const void* q, const void* k, const void* v, void* o, float* ls
 
 int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, float* lse, int B,
                       int H, int Nq, int Nkv, int D, int dtype, int causal, float scale) {
-  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr)
-    return fail(FA_ERR_INVALID_ARG, "q, k, v and o must not be null");
-  Problem chk{};
-  chk.B = B; chk.H = H; chk.Nq = Nq; chk.Nkv = Nkv; chk.D = D; chk.dtype = dtype;
-  chk.causal = causal; chk.scale = scale;
-  const int64_t qs[4] = {int64_t(H) * Nq * D, int64_t(Nq) * D, D, 1};
-  const int64_t ks[4] = {int64_t(H) * Nkv * D, int64_t(Nkv) * D, D, 1};
-  int rc = validate(chk, qs, ks, ks, qs);
-  if (rc) return rc;
-  int dev;
-  if ((rc = check_device(&dev))) return rc;
-  if (dev >= 64) return fail(FA_ERR_UNSUPPORTED, "device ordinal >= 64");
+  return host_call(q, k, v, o, lse, B, H, Nq, Nkv, D, dtype, causal, scale, true);
+}
 
+int fa_fwd_sm100_host_async(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                            int H, int Nq, int Nkv, int D, int dtype, int causal, float scale) {
+  return host_call(q, k, v, o, lse, B, H, Nq, Nkv, D, dtype, causal, scale, false);
+}
+
+int fa_host_sync(void) {
+  int dev;
+  int rc = check_device(&dev);
+  if (rc) return rc;
+  if (dev >= 64) return FA_OK;
   HostWs& w = g_ws[dev];
   std::lock_guard<std::mutex> lk(w.mu);
-  if (!w.init) {
-    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
-    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_run, cudaStreamNonBlocking));
-    FA_CUDA_TRY(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
-    w.init = true;
-  }
-  const size_t heads = size_t(B) * H;
-  const size_t q_head = size_t(Nq) * D * 2, kv_head = size_t(Nkv) * D * 2;
-  const size_t bytes_q = heads * q_head, bytes_kv = heads * kv_head;
-  const size_t bytes_lse = heads * Nq * sizeof(float);
-  if (w.cap_q < bytes_q) {
-    if (w.dq) cudaFree(w.dq);
-    if (w.dout) cudaFree(w.dout);
-    w.dq = w.dout = nullptr; w.cap_q = 0;
-    FA_CUDA_TRY(cudaMalloc(&w.dq, bytes_q));
-    FA_CUDA_TRY(cudaMalloc(&w.dout, bytes_q));
-    w.cap_q = bytes_q;
-  }
-  if (w.cap_kv < bytes_kv) {
-    if (w.dk) cudaFree(w.dk);
-    if (w.dv) cudaFree(w.dv);
-    w.dk = w.dv = nullptr; w.cap_kv = 0;
-    FA_CUDA_TRY(cudaMalloc(&w.dk, bytes_kv));
-    FA_CUDA_TRY(cudaMalloc(&w.dv, bytes_kv));
-    w.cap_kv = bytes_kv;
-  }
-  if (lse != nullptr && w.cap_lse < bytes_lse) {
-    if (w.dlse) cudaFree(w.dlse);
-    w.dlse = nullptr; w.cap_lse = 0;
-    FA_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w.dlse), bytes_lse));
-    w.cap_lse = bytes_lse;
-  }
-
-  // chunk over the flattened (b,h) axis: heads are independent and contiguous in [B,H,N,D]
-  const std::vector<size_t> chunk_heads = plan_host_chunks(heads, Nq, Nkv, D, causal);
-  const size_t n_chunks = chunk_heads.size();
-  while (w.ev_in.size() < n_chunks) {
-    cudaEvent_t e1, e2;
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-    w.ev_in.push_back(e1);
-    w.ev_run.push_back(e2);
-  }
-
-  // FA_HOST_TIMING=1: print host enqueue time, device span and total per call (diagnostic)
-  static const bool timing = std::getenv("FA_HOST_TIMING") != nullptr;
-  static cudaEvent_t t_ev[2] = {nullptr, nullptr};
-  static std::vector<cudaEvent_t> t_chunk;
-  const auto t_cpu0 = std::chrono::steady_clock::now();
-  if (timing) {
-    if (t_ev[0] == nullptr) { cudaEventCreate(&t_ev[0]); cudaEventCreate(&t_ev[1]); }
-    cudaEventRecord(t_ev[0], w.s_in);
-  }
-  const char* hq = static_cast<const char*>(q);
-  const char* hk = static_cast<const char*>(k);
-  const char* hv = static_cast<const char*>(v);
-  char* ho = static_cast<char*>(o);
-  size_t h0 = 0;
-  for (size_t c = 0; c < n_chunks; h0 += chunk_heads[c], ++c) {
-    const size_t nh = chunk_heads[c];
-    char* dq = static_cast<char*>(w.dq) + h0 * q_head;
-    char* dk = static_cast<char*>(w.dk) + h0 * kv_head;
-    char* dv = static_cast<char*>(w.dv) + h0 * kv_head;
-    char* dout = static_cast<char*>(w.dout) + h0 * q_head;
-    FA_CUDA_TRY(cudaMemcpyAsync(dq, hq + h0 * q_head, nh * q_head, cudaMemcpyHostToDevice, w.s_in));
-    FA_CUDA_TRY(cudaMemcpyAsync(dk, hk + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
-    FA_CUDA_TRY(cudaMemcpyAsync(dv, hv + h0 * kv_head, nh * kv_head, cudaMemcpyHostToDevice, w.s_in));
-    FA_CUDA_TRY(cudaEventRecord(w.ev_in[c], w.s_in));
-    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_run, w.ev_in[c], 0));
-    if (timing) {
-      while (t_chunk.size() < 4 * (c + 1)) { cudaEvent_t e; cudaEventCreate(&e); t_chunk.push_back(e); }
-      cudaEventRecord(t_chunk[4 * c + 0], w.s_in);
-      cudaEventRecord(t_chunk[4 * c + 1], w.s_run);
-    }
-    // the chunk is a [1, nh, N, D] problem
-    Problem p{};
-    p.B = 1; p.H = static_cast<int>(nh); p.Nq = Nq; p.Nkv = Nkv; p.D = D; p.dtype = dtype;
-    p.causal = causal; p.scale = scale;
-    const int64_t cqs[4] = {int64_t(nh) * Nq * D, int64_t(Nq) * D, D, 1};
-    const int64_t cks[4] = {int64_t(nh) * Nkv * D, int64_t(Nkv) * D, D, 1};
-    if ((rc = validate(p, cqs, cks, cks, cqs))) return rc;
-    float* dl = (lse != nullptr) ? w.dlse + h0 * Nq : nullptr;
-    if ((rc = run_device(dq, dk, dv, dout, dl, p, w.s_run))) return rc;
-    FA_CUDA_TRY(cudaEventRecord(w.ev_run[c], w.s_run));
-    if (timing) cudaEventRecord(t_chunk[4 * c + 2], w.s_run);
-    FA_CUDA_TRY(cudaStreamWaitEvent(w.s_out, w.ev_run[c], 0));
-    FA_CUDA_TRY(cudaMemcpyAsync(ho + h0 * q_head, dout, nh * q_head, cudaMemcpyDeviceToHost, w.s_out));
-    if (lse != nullptr)
-      FA_CUDA_TRY(cudaMemcpyAsync(lse + h0 * Nq, dl, nh * Nq * sizeof(float),
-                                  cudaMemcpyDeviceToHost, w.s_out));
-    if (timing) cudaEventRecord(t_chunk[4 * c + 3], w.s_out);
-  }
-  const auto t_cpu1 = std::chrono::steady_clock::now();
-  if (timing) cudaEventRecord(t_ev[1], w.s_out);
-  FA_CUDA_TRY(cudaStreamSynchronize(w.s_out));
-  if (timing) {
-    const auto t_cpu2 = std::chrono::steady_clock::now();
-    float dev_ms = 0.f;
-    cudaEventElapsedTime(&dev_ms, t_ev[0], t_ev[1]);
-    fprintf(stderr, "[fa_fwd_sm100_host] N=%d chunks=%zu enqueue %.3f ms, device span %.3f ms, total %.3f ms\n",
-            Nq, n_chunks, std::chrono::duration<double, std::milli>(t_cpu1 - t_cpu0).count(), dev_ms,
-            std::chrono::duration<double, std::milli>(t_cpu2 - t_cpu0).count());
-    for (size_t c = 0; c < n_chunks; ++c) {
-      float t[4];
-      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], t_ev[0], t_chunk[4 * c + i]);
-      fprintf(stderr, "    chunk %zu: H2D done %.3f, kernel start %.3f, kernel done %.3f, D2H done %.3f\n", c,
-              t[0], t[1], t[2], t[3]);
-    }
-  }
+  if (w.s_out != nullptr) FA_CUDA_TRY(cudaStreamSynchronize(w.s_out));
   return FA_OK;
 }
 
@@ -1061,13 +1189,17 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
 
   // 2. main kernel
   BwdMaps m;
-  if ((rc = make_map(&m.q, q, B, H, Nq, D, p.qs, dtype, fa::kTileM))) return rc;
-  if ((rc = make_map(&m.k, k, B, H, Nkv, D, p.ks, dtype, fa::kTileN))) return rc;
-  if ((rc = make_map(&m.v, v, B, H, Nkv, D, p.vs, dtype, fa::kTileN))) return rc;
-  if ((rc = make_map(&m.d_o, d_o, B, H, Nq, D, dos, dtype, fa::kTileM))) return rc;
-  if ((rc = make_map(&m.dk, dk, B, H, Nkv, D, dks, dtype, fa::kTileN))) return rc;
-  if ((rc = make_map(&m.dv, dv, B, H, Nkv, D, dvs, dtype, fa::kTileN))) return rc;
-  if ((rc = make_map_dq(&m.dq, dq_accum, B * H, Nq, D))) return rc;
+  BwdPlan key{};
+  const void* ptrs[7] = {q, k, v, d_o, dk, dv, dq_accum};
+  memcpy(key.ptr, ptrs, sizeof ptrs);
+  key.B = B; key.H = H; key.Nq = Nq; key.Nkv = Nkv; key.D = D; key.dtype = dtype; key.device = dev;
+  memcpy(key.st[0], p.qs, sizeof p.qs);
+  memcpy(key.st[1], p.ks, sizeof p.ks);
+  memcpy(key.st[2], p.vs, sizeof p.vs);
+  memcpy(key.st[3], dos, sizeof dos);
+  memcpy(key.st[4], dks, sizeof dks);
+  memcpy(key.st[5], dvs, sizeof dvs);
+  if ((rc = g_bwd_plans.get(key, &m))) return rc;
   fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale};
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 
@@ -1088,8 +1220,12 @@ int fa_host_workspace_release(void) {
   int rc = check_device(&dev);
   if (rc) return rc;
   if (dev >= 64) return FA_OK;
-  std::lock_guard<std::mutex> lk(g_ws[dev].mu);
-  return ws_release(g_ws[dev]);
+  {
+    std::lock_guard<std::mutex> lk(g_ws[dev].mu);
+    ws_release(g_ws[dev]);
+  }
+  release_sk_workspaces(dev);
+  return FA_OK;
 }
 
 int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mode, uint32_t lbo,

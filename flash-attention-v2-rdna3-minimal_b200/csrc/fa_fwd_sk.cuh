@@ -1,23 +1,33 @@
 // Persistent "stream-K" variant of the warp-specialised forward kernel (non-causal, Nq % 256 == 0).
 //
 // Why: fa_fwd_ws_kernel runs one CTA per 256-row query block, so a launch with U blocks on G = 148 SMs
-// takes ceil(U / G) rounds: B=1, H=16 gives 256 blocks at N=4096 (2 rounds for 1.73 rounds of work,
-// 15 % lost) and 512 at N=8192 (4 rounds for 3.46).  Here the work is linearised as
-// (unit, KV tile) items, unit = (batch, head, 256-row block) with T = ceil(Nkv / 128) items each, and
-// the grid is G persistent CTAs.  The first floor(U / G) - 1 rounds are data-parallel (CTA c takes unit
-// round * G + c: the CTAs of a round work on neighbouring heads, so K/V stays L2-resident as in the
+// takes ceil(U / G) rounds: B=1, H=16 gives 128 blocks at N=2048 (one round on 128 of 148 SMs), 256 at
+// N=4096 (2 rounds for 1.73 rounds of work) and 512 at N=8192 (4 rounds for 3.46).  Here the work is
+// linearised as (unit, KV tile) items, unit = (batch, head, 256-row block) with T = ceil(Nkv / 128) items
+// each, and the grid is min(G, items) persistent CTAs.  The first sk_dp rounds are data-parallel (CTA c takes
+// unit round * G + c: the CTAs of a round work on neighbouring heads, so K/V stays L2-resident as in the
 // one-shot kernel - splitting ALL units contiguously made every CTA stream a different head and was
-// HBM-bound at N=16384).  The last G + U % G units are split evenly: CTA c takes the contiguous range
-// [c W / G, (c+1) W / G) of their W items, so every SM gets the same number of KV tiles (+-1); and
-// every CTA pays the prologue (TMEM allocation, barrier initialisation, descriptor prefetch) once.  A range covers a tail part of one unit, whole units,
-// and a head part of another (ranges are at least T long, checked by the launcher), so a unit is
-// shared by at most two CTAs:
-//   * the CTA that owns the TAIL part (KV tiles t0..T-1, the first thing it does) stores its
-//     unnormalised O, m and l to a per-CTA workspace slot and raises a flag;
-//   * the CTA that owns the HEAD part (KV tiles 0..t1-1, the last thing it does) waits for the flag of
-//     the next CTA, merges  O = O_a 2^((m_a-M)c) + O_b 2^((m_b-M)c),  l likewise, M = max(m_a, m_b),
-//     normalises, stores, and lowers the flag again (so launches and CUDA-graph replays start clean).
-// No deadlock: producers never wait on anything; consumers wait at the very end of their range.
+// HBM-bound at N=16384).  The remaining units are split evenly: CTA c takes the contiguous range
+// [c W / G, (c+1) W / G) of their W items, so every SM gets the same number of KV tiles (+-1), and every
+// CTA pays the prologue (TMEM allocation, barrier initialisation, descriptor prefetch) once.
+//
+// A range is a sequence of SEGMENTS, one per unit it touches:
+//   * a segment that does not start at KV tile 0 (a tail or interior part; only ever the FIRST segment of a
+//     CTA) is a PRODUCER part: unnormalised O, m and l go to the CTA's workspace slot, then a flag is raised;
+//   * a segment that starts at tile 0 but stops short of T (only ever the LAST segment of a CTA) is the
+//     CONSUMER part: it waits for the flags of the CTAs that own the rest of the unit (cta+1, cta+2, ... -
+//     ranges shorter than a unit are allowed, so there can be several), merges
+//       O = sum_i O_i 2^((m_i-M)c),  l likewise,  M = max_i m_i,
+//     normalises, stores, and lowers the flags again (so launches and CUDA-graph replays start clean);
+//   * anything else is a whole unit.
+// No deadlock: producers never wait on another CTA; consumers wait at the very end of their range.
+//
+// Unit boundaries inside a CTA are pipelined (round 2): Q has its own buffers and O its own staging tile,
+// so the next unit's Q is fetched as soon as the last S product of the current unit has read the old one
+// (bar_q_free, a tcgen05.commit), its first S is issued right behind the current unit's last PV, and the only
+// thing the tensor cores wait for at a boundary is the read-out of O from tensor memory (bar_tile_free).
+// Partials are laid out so that every warp-level access of the exchange is one contiguous 512-byte run
+// ([tile][half][float4 index][row]): the row-major layout of round 1 cost 8x the LSU wavefronts.
 //
 // Everything per KV tile - roles, barriers, TMEM layout, the softmax step - is that of
 // fa_fwd_ws.cuh; barrier parities run on counters that continue across the units of a CTA.
@@ -26,34 +36,63 @@
 
 namespace fa {
 
-// workspace slot of one CTA: unnormalised O of both tiles (fp32), then (m, l) per row
+// workspace slot of one CTA: unnormalised O of both tiles (fp32, [tile][half][kDP/8 float4s][128 rows]),
+// then (m, l) per row
 template <int kDP>
 struct SkSlot {
   static constexpr int kOFloats = 2 * kTileM * kDP;
   static constexpr int kFloats = kOFloats + 2 * kTileM * 2;
 };
+constexpr int kSkSlotFloatsMax = SkSlot<128>::kFloats;
 
-// Shared memory: Q tiles (optionally double-buffered, see FA_SK_QDOUBLE), the K/V ring, barriers and
-// a single-buffered row-max exchange.  No alignment slack: the dynamic shared-memory window starts
-// 1024-byte aligned (checked at kernel start).
-// FA_SK_QDOUBLE=1 double-buffers the Q tiles (next unit's Q and first S under the current unit's
-// epilogue) at the price of a 3-deep instead of 4-deep K/V ring at D = 128.  Measured with the
-// three-part P hand-off: the deeper ring wins by 1-3 % at every sweep length, so the default is 0.
-#ifndef FA_SK_QDOUBLE
-#define FA_SK_QDOUBLE 0
-#endif
-constexpr bool kSkQDouble = FA_SK_QDOUBLE != 0;
-
+// Shared memory: 2 Q tiles, the K/V ring, ONE O staging tile (shared by the two Q tiles, which finish half a
+// step apart), barriers and a single-buffered row-max exchange.  No alignment slack: the dynamic
+// shared-memory window starts 1024-byte aligned (checked at kernel start).
 template <int kDP>
 struct SkCfg {
   static constexpr int kTileBytes = kTileM * kDP * 2;
-  static constexpr int kStages = (kDP == 128) ? (kSkQDouble ? 3 : 4) : 8;
-  static constexpr int kQ = 0;                          // [2 buffers][2 tiles]; also O staging
-  static constexpr int kKV = kQ + (kSkQDouble ? 4 : 2) * kTileBytes;
-  static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 18 + 2 * kStages;
+  static constexpr int kStages = (kDP == 128) ? 4 : 8;
+  static constexpr int kQ = 0;
+  static constexpr int kKV = kQ + 2 * kTileBytes;
+  static constexpr int kStage = kKV + kStages * kTileBytes;  // O staging
+  static constexpr int kBars = kStage + kTileBytes;
+  static constexpr int kNumBars = 17 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;  // float [2 tile][2 half][128]; also row sums
   static constexpr int kTotal = kMax + 2 * 2 * 128 * 4;
+  static_assert(kTotal <= 232448, "shared memory budget");
+};
+
+// Segment walker: the same sequence in every role.  First `dp` whole units in round-robin order, then the
+// stream-K range of this CTA over the remaining units.
+struct SkWalker {
+  int dp, round, u, t0, rem, cta, G, T;
+  __device__ __forceinline__ void init(const TcParams& p, int cta_, int G_) {
+    cta = cta_;
+    G = G_;
+    T = p.sk_T;
+    dp = p.sk_dp;
+    round = 0;
+    const long long pos_begin = p.sk_W * cta / G;
+    const long long pos_end = p.sk_W * (cta + 1) / G;
+    const int u_rel = static_cast<int>(pos_begin / T);
+    u = p.sk_dp * G + u_rel;
+    t0 = static_cast<int>(pos_begin - static_cast<long long>(u_rel) * T);
+    rem = static_cast<int>(pos_end - pos_begin);
+  }
+  __device__ __forceinline__ bool more() const { return dp > 0 || rem > 0; }
+  __device__ __forceinline__ int unit() const { return dp > 0 ? round * G + cta : u; }
+  __device__ __forceinline__ int first() const { return dp > 0 ? 0 : t0; }
+  __device__ __forceinline__ int count() const { return dp > 0 ? T : min(T - t0, rem); }
+  __device__ __forceinline__ void next() {
+    if (dp > 0) {
+      --dp;
+      ++round;
+    } else {
+      rem -= min(T - t0, rem);
+      u += 1;
+      t0 = 0;
+    }
+  }
 };
 
 template <int kDP, bool kBF16>
@@ -67,6 +106,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kDBlocks = kDP / 64;
   constexpr int kKSteps = kDP / 16;
   constexpr int kOHalf = kDP / 2;
+  constexpr int kQ4 = kOHalf / 4;  // float4s of a partial row-half
   auto col_s = [](int t) -> uint32_t { return static_cast<uint32_t>(t) * 128u; };
   auto col_o = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u; };
 
@@ -75,23 +115,28 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // SkCfg has no alignment slack
   const uint32_t sQ = smem_u32(smem + C::kQ);
   const uint32_t sKV = smem_u32(smem + C::kKV);
+  const uint32_t sStage = smem_u32(smem + C::kStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kBars + 8 * C::kNumBars);
   float* sMax = reinterpret_cast<float*>(smem + C::kMax);
   float* sFinal = sMax;  // row sums are exchanged between KV passes, row maxima inside them
 
-  // barrier map
-  auto bar_q_full = [&](int buf, int t) { return smem_u32(&bars[12 + buf * 2 + t]); };  // tx, count 1
-  auto bar_s_full = [&](int t) { return smem_u32(&bars[2 + t]); };      // tcgen05.commit
-  auto bar_p_early = [&](int t) { return smem_u32(&bars[4 + t]); };     // 8 softmax warps
-  auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };      // 8 softmax warps
-  auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
-  // per tile, 8 softmax warps: "O_t has been read out of TMEM and the Q_t buffer (O staging) is
-  // free again" - gates the Q load and the first PV of the next unit
+  // barrier map.  "per item": one phase per KV tile this CTA processes; "per segment": one per unit part
+  auto bar_q_full = [&](int t) { return smem_u32(&bars[t]); };           // tx, count 1; per segment
+  auto bar_s_full = [&](int t) { return smem_u32(&bars[2 + t]); };       // tcgen05.commit; per item
+  auto bar_p_early = [&](int t) { return smem_u32(&bars[4 + t]); };      // 8 softmax warps; per item
+  auto bar_p_late = [&](int t) { return smem_u32(&bars[6 + t]); };       // 8 softmax warps; per item
+  auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };      // tcgen05.commit; per segment
+  // 8 softmax warps, per segment: "O_t has been read out of tensor memory" - gates the first PV of the
+  // next segment
   auto bar_tile_free = [&](int t) { return smem_u32(&bars[10 + t]); };
-  auto bar_p_mid = [&](int t) { return smem_u32(&bars[16 + 2 * kS + t]); };  // 8 softmax warps
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[16 + s]); };    // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[16 + kS + s]); };  // tcgen05.commit
+  auto bar_p_mid = [&](int t) { return smem_u32(&bars[12 + t]); };       // 8 softmax warps; per item
+  // tcgen05.commit behind the last S_t product of a segment: the Q_t buffer may be reloaded; per segment
+  auto bar_q_free = [&](int t) { return smem_u32(&bars[14 + t]); };
+  // count 1: the O staging tile is free again; one phase per use, uses numbered 2 * segment + tile
+  const uint32_t bar_stage = smem_u32(&bars[16]);
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[17 + s]); };     // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[17 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -99,47 +144,27 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int cta = blockIdx.x;
   const int G = gridDim.x;
   const int T = p.sk_T;
-  // Segment walker, the same sequence in every role (32-bit state).  First sk_dp whole units in
-  // round-robin order (unit = round * G + cta: the CTAs of a round share heads, so K/V tiles are
-  // re-used in L2 exactly as in the one-shot kernel), then the stream-K range of this CTA over the
-  // remaining units.  kind 0 = whole unit, 1 = tail part (producer), 2 = head part (consumer).
-  int w_dp = p.sk_dp, w_round = 0;
-  int w_u, w_t0, w_rem;
-  {
-    const long long pos_begin = p.sk_W * cta / G;
-    const long long pos_end = p.sk_W * (cta + 1) / G;
-    const int u_rel = static_cast<int>(pos_begin / T);
-    w_u = p.sk_dp * G + u_rel;
-    w_t0 = static_cast<int>(pos_begin - static_cast<long long>(u_rel) * T);
-    w_rem = static_cast<int>(pos_end - pos_begin);
-  }
-  auto seg_more = [&]() { return w_dp > 0 || w_rem > 0; };
-  auto seg_unit = [&]() { return w_dp > 0 ? w_round * G + cta : w_u; };
-  auto seg_t0 = [&]() { return w_dp > 0 ? 0 : w_t0; };
-  auto seg_n = [&]() { return w_dp > 0 ? T : min(T - w_t0, w_rem); };
-  auto seg_next = [&](int n) {
-    if (w_dp > 0) {
-      --w_dp;
-      ++w_round;
-    } else {
-      w_rem -= n;
-      w_u += 1;
-      w_t0 = 0;
-    }
+  SkWalker wk;
+  wk.init(p, cta, G);
+  auto unit_coords = [&](int unit, int& row0, int& hh, int& bb) {
+    row0 = (unit % p.sk_P) * 2 * kTileM;
+    hh = (unit / p.sk_P) % p.H;
+    bb = (unit / p.sk_P) / p.H;
   };
 
   if (warp == 16 && lane == 0) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_q_full(0, t), 1);
-      mbar_init(bar_q_full(1, t), 1);
+      mbar_init(bar_q_full(t), 1);
       mbar_init(bar_s_full(t), 1);
       mbar_init(bar_p_early(t), 8);
       mbar_init(bar_p_late(t), 8);
       mbar_init(bar_o_final(t), 1);
       mbar_init(bar_tile_free(t), 8);
       mbar_init(bar_p_mid(t), 8);
+      mbar_init(bar_q_free(t), 1);
     }
+    mbar_init(bar_stage, 1);
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
       mbar_init(bar_kv_full(s), 1);
@@ -152,6 +177,23 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
+    if (wk.more()) {  // first segment's Q tiles and first ring-full of K/V -> L2 before pdl_wait() (fa_fwd_ws.cuh)
+      int row0, hh, bb;
+      unit_coords(wk.unit(), row0, hh, bb);
+      const int t0 = wk.first(), n = wk.count();
+#pragma unroll
+      for (int db = 0; db < kDBlocks; ++db) {
+        tma_prefetch_l2_4d(&tmap_q, db * 64, row0, hh, bb);
+        tma_prefetch_l2_4d(&tmap_q, db * 64, row0 + kTileM, hh, bb);
+#pragma unroll
+        for (int j = 0; j < kS / 2; ++j) {
+          if (j < n) {
+            tma_prefetch_l2_4d(&tmap_k, db * 64, (t0 + j) * kTileN, hh, bb);
+            tma_prefetch_l2_4d(&tmap_v, db * 64, (t0 + j) * kTileN, hh, bb);
+          }
+        }
+      }
+    }
   }
   if (warp == 16) {
     tmem_alloc(smem_u32(tmem_slot), 512);
@@ -160,44 +202,39 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory (inputs, the workspace and
+  // its flags, which consecutive launches on a stream share) is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   if (*tmem_slot != 0u) __trap();  // see fa_fwd_ws.cuh: constant TMEM addresses
   constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;
 
   if (warp >= 16) {
-    setmaxnreg_dec<56>();  // 512 x 104 + 128 x 56 <= 640 x 96 (the walker state does not fit in 32)
+    setmaxnreg_dec<64>();  // 512 x 104 + 128 x 64 = 640 x 96 (the walker state does not fit in 32)
     if (warp == 17) {
       // =======================================================================================
       // TMA producer
       // =======================================================================================
       if (elect_one()) {
         int kvi = 0;  // running K/V ring index (K and V alternate)
-        // Q tiles of segment `sgi` (its unit is `unit`) -> buffer sgi & 1.  The buffer was the O
-        // staging of segment sgi - 2: wait until that store has read it.
-        auto load_q = [&](int sgi, int unit) {
-          const int buf = kSkQDouble ? (sgi & 1) : 0;
-          const int lag = kSkQDouble ? 2 : 1;  // the buffer was the O staging of segment sgi - lag
-          const int row0 = (unit % p.sk_P) * 2 * kTileM;
-          const int hh = (unit / p.sk_P) % p.H;
-          const int bb = (unit / p.sk_P) / p.H;
+        for (int seg = 0; wk.more(); ++seg) {
+          const int n = wk.count();
+          const int t0 = wk.first();
+          int row0, hh, bb;
+          unit_coords(wk.unit(), row0, hh, bb);
+          // Q tiles of this segment; the buffers were last read by the final S products of segment seg - 1
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (sgi >= lag) mbar_wait(bar_tile_free(t), (sgi - lag) & 1, 21);
-            mbar_arrive_expect_tx(bar_q_full(buf, t), C::kTileBytes);
+            if (seg > 0) mbar_wait(bar_q_free(t), (seg - 1) & 1, 21);
+            mbar_arrive_expect_tx(bar_q_full(t), C::kTileBytes);
 #pragma unroll
             for (int db = 0; db < kDBlocks; ++db)
-              tma_load_4d(sQ + (buf * 2 + t) * C::kTileBytes + db * 16384, &tmap_q, bar_q_full(buf, t),
-                          db * 64, row0 + t * kTileM, hh, bb);
+              tma_load_4d(sQ + t * C::kTileBytes + db * 16384, &tmap_q, bar_q_full(t), db * 64,
+                          row0 + t * kTileM, hh, bb);
           }
-        };
-        if (kSkQDouble && seg_more()) load_q(0, seg_unit());
-        for (int seg = 0; seg_more(); ++seg) {
-          const int n = seg_n();
-          const int t0 = seg_t0();
-          const int unit = seg_unit();
-          const int hh = (unit / p.sk_P) % p.H;
-          const int bb = (unit / p.sk_P) / p.H;
-          auto load_kv = [&](int x) {  // ring order K V K V ...
+#pragma unroll 1
+          for (int x = 0; x < 2 * n; ++x, ++kvi) {  // ring order K V K V ...
             const int slot = kvi % kS;
             const uint32_t use = kvi / kS;
             mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
@@ -207,24 +244,16 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             for (int db = 0; db < kDBlocks; ++db)
               tma_load_4d(sKV + slot * C::kTileBytes + db * 16384, map, bar_kv_full(slot), db * 64,
                           (t0 + (x >> 1)) * kTileN, hh, bb);
-            ++kvi;
-          };
-          // a ring-full of this unit's K/V first, then the NEXT unit's Q (its buffer frees up when
-          // the previous unit's epilogue, which runs as this unit starts, has been stored)
-          const int pre = min(2 * n, kS);
-#pragma unroll 1
-          for (int x = 0; x < pre; ++x) load_kv(x);
-          if (!kSkQDouble) load_q(seg, unit);
-          seg_next(n);
-          if (kSkQDouble && seg_more()) load_q(seg + 1, seg_unit());
-#pragma unroll 1
-          for (int x = pre; x < 2 * n; ++x) load_kv(x);
+          }
+          wk.next();
         }
       }
       __syncwarp();
     } else if (warp == 16) {
       // =======================================================================================
-      // MMA issuer
+      // MMA issuer.  One continuous sequence over all KV tiles of the CTA:
+      //   S0 S1 | PV0(g) S0(g+1) PV1(g) S1(g+1) | ...
+      // where item g+1 may belong to the next segment (its S then reads the next unit's Q tiles).
       // =======================================================================================
       if (elect_one()) {
         constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);
@@ -235,21 +264,23 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc_fence_after();
         };
         auto release_kv = [&](int idx) { tc_commit(bar_kv_empty(idx % kS)); };
-        auto issue_s = [&](int qbuf, int t, int kidx) {  // S_t = Q_t K^T, K in ring position kidx
+        // S_t = Q_t K^T, K in ring position kidx; `last_of_seg`: no later product of this segment reads Q_t
+        auto issue_s = [&](int t, int kidx, bool last_of_seg) {
           const uint32_t k_lo = smem_desc_lo(sKV + (kidx % kS) * C::kTileBytes, 16);
-          const uint32_t q_lo = smem_desc_lo(sQ + (qbuf * 2 + t) * C::kTileBytes, 16);
+          const uint32_t q_lo = smem_desc_lo(sQ + t * C::kTileBytes, 16);
 #pragma unroll
           for (int k = 0; k < kKSteps; ++k) {
             const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
             umma_ss2(tmem + col_s(t), q_lo + off, desc_hi, k_lo + off, desc_hi, idesc_s, k > 0);
           }
           tc_commit(bar_s_full(t));
+          if (last_of_seg) tc_commit(bar_q_free(t));
         };
         auto pv_step = [&](int t, uint32_t v_lo, int ks, uint32_t acc) {
           umma_ts2(tmem + col_o(t), tmem + col_s(t) + (ks >> 2) * 64 + (ks & 3) * 8,
                    v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
         };
-        // g = running KV-tile count of this CTA (parity source of the per-tile barriers)
+        // g = running KV-tile count of this CTA (parity source of the per-item barriers)
         auto issue_pv = [&](int t, int vidx, int g, bool first, bool last) {
           const uint32_t v_lo = smem_desc_lo(sKV + (vidx % kS) * C::kTileBytes, 16384);
           mbar_wait(bar_p_early(t), g & 1, 31 + t);
@@ -279,30 +310,43 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         };
 
         int g = 0;  // KV tiles processed so far by this CTA; ring indices are 2g (K) and 2g+1 (V)
-        for (int seg = 0; seg_more(); ++seg) {
-          const int n = seg_n();
-          const int qb = kSkQDouble ? (seg & 1) : 0;
-          wait_kv(2 * g);
+        if (wk.more()) {
+          const int n0 = wk.count();
+          wait_kv(0);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(bar_q_full(qb, t), kSkQDouble ? ((seg >> 1) & 1) : (seg & 1), 33);
+            mbar_wait(bar_q_full(t), 0, 33);
             tc_fence_after();
-            issue_s(qb, t, 2 * g);
+            issue_s(t, 0, n0 == 1);
           }
-          release_kv(2 * g);
+          release_kv(0);
+        }
+        for (int seg = 0; wk.more(); ++seg) {
+          const int n = wk.count();
+          wk.next();
+          const bool more_segs = wk.more();
+          const int n_next = more_segs ? wk.count() : 0;
 #pragma unroll 1
           for (int j = 0; j < n; ++j, ++g) {
             const bool first = (j == 0), last = (j == n - 1);
+            // what follows item g: item j+1 of this segment, item 0 of the next one, or nothing
+            const bool has_next = !last || more_segs;
+            const bool next_is_new_seg = last && more_segs;
+            const bool next_last_s = last ? (n_next == 1) : (j + 1 == n - 1);
             wait_kv(2 * g + 1);
-            // O_t of the previous unit must have left TMEM before the first PV overwrites it
+            // O_t of the previous segment must have left TMEM before the first PV overwrites it
             if (first && seg > 0) {
               mbar_wait(bar_tile_free(0), (seg - 1) & 1, 36);
               tc_fence_after();
             }
             issue_pv(0, 2 * g + 1, g, first, last);
-            if (!last) {
+            if (has_next) {
               wait_kv(2 * g + 2);
-              issue_s(qb, 0, 2 * g + 2);
+              if (next_is_new_seg) {
+                mbar_wait(bar_q_full(0), (seg + 1) & 1, 33);
+                tc_fence_after();
+              }
+              issue_s(0, 2 * g + 2, next_last_s);
             }
             if (first && seg > 0) {
               mbar_wait(bar_tile_free(1), (seg - 1) & 1, 37);
@@ -310,12 +354,15 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             }
             issue_pv(1, 2 * g + 1, g, first, last);
             release_kv(2 * g + 1);
-            if (!last) {
-              issue_s(qb, 1, 2 * g + 2);
+            if (has_next) {
+              if (next_is_new_seg) {
+                mbar_wait(bar_q_full(1), (seg + 1) & 1, 34);
+                tc_fence_after();
+              }
+              issue_s(1, 2 * g + 2, next_last_s);
               release_kv(2 * g + 2);
             }
           }
-          seg_next(n);
         }
       }
       __syncwarp();
@@ -336,14 +383,19 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float* my_max = sMax + (t * 2 + half) * 128 + r;
     const float* other_max = sMax + (t * 2 + (half ^ 1)) * 128 + r;
     const bool tile_leader = ((warp & 7) == 0) && lane == 0;
+    // my float4 column q of a partial lives at part_o[q * 128] (see SkSlot)
+    const size_t part_o_off = (static_cast<size_t>((t * 2 + half) * kQ4) * 128 + r) * 4;
+    const size_t part_ml_off = SkSlot<kDP>::kOFloats + (t * kTileM + r) * 2;
 
     int g = 0;
-    for (int seg = 0; seg_more(); ++seg) {
-      const int n = seg_n();
-      const int t0 = seg_t0();
+    for (int seg = 0; wk.more(); ++seg) {
+      const int n = wk.count();
+      const int t0 = wk.first();
       const int kind = (t0 > 0) ? 1 : (n < T ? 2 : 0);
-      const int unit = seg_unit();
-      const int tile_row0 = (unit % p.sk_P) * 2 * kTileM + t * kTileM;
+      const int unit = wk.unit();
+      int row0, hh, bb;
+      unit_coords(unit, row0, hh, bb);
+      const int tile_row0 = row0 + t * kTileM;
       float m_run = -INFINITY;
       float l_run = 0.f;
 
@@ -365,13 +417,14 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       named_bar_sync(pair_bar, 64);
       float l_tot = l_run + sFinal[(t * 2 + (half ^ 1)) * 128 + r];
       const int row = tile_row0 + r;
+      const int use = 2 * seg + t;  // my turn on the O staging tile
       mbar_wait(bar_o_final(t), seg & 1, 54 + t);
       tc_fence_after();
 
       if (kind == 1) {
         // producer: unnormalised O row-half, and (m, l) by the half-0 thread, to my workspace slot
         float* slot = p.sk_ws + static_cast<size_t>(cta) * SkSlot<kDP>::kFloats;
-        float* o_dst = slot + (t * kTileM + r) * kDP + half * kOHalf;
+        float4* o_dst = reinterpret_cast<float4*>(slot + part_o_off);
 #pragma unroll
         for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
           uint32_t o[32];
@@ -379,68 +432,90 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tmem_wait_ld();
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
-            __stcg(reinterpret_cast<float4*>(o_dst + cidx * 32 + e),
+            __stcg(o_dst + (cidx * 8 + (e >> 2)) * 128,
                    make_float4(__uint_as_float(o[e]), __uint_as_float(o[e + 1]),
                                __uint_as_float(o[e + 2]), __uint_as_float(o[e + 3])));
         }
-        if (half == 0) {
-          float* ml = slot + SkSlot<kDP>::kOFloats + (t * kTileM + r) * 2;
-          __stcg(reinterpret_cast<float2*>(ml), make_float2(m_run, l_tot));
-        }
-        __threadfence();
+        // O_t has left tensor memory: the next segment's first PV may overwrite it
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tile_free(t));
+        if (half == 0) __stcg(reinterpret_cast<float2*>(slot + part_ml_off), make_float2(m_run, l_tot));
+        __threadfence();
         named_bar_sync(tile_bar, 256);
         if (tile_leader) {
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + cta * 2 + t), "r"(1)
                        : "memory");
+          // pass my turn on the staging tile on (a producer part does not use it)
+          if (use > 0) mbar_wait(bar_stage, (use - 1) & 1, 56);
+          mbar_arrive(bar_stage);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tile_free(t));
       } else {
-        float scale_mine = 1.f, scale_other = 0.f;
-        const float* o_src = nullptr;
+        float f_mine = 1.f;
+        int parts = 0;  // producer parts of my unit: CTAs cta+1 .. cta+parts
         if (kind == 2) {
-          // consumer: wait for the partial of the tail part (owned by the next CTA), merge
-          int* flag = p.sk_flags + (cta + 1) * 2 + t;
+          const long long unit_end = static_cast<long long>(unit - p.sk_dp * G + 1) * T;
+          for (int c2 = cta + 1; c2 < G && p.sk_W * c2 / G < unit_end; ++c2) ++parts;
+          // wait for the partials of the rest of the unit, then find the common maximum and the row sum
           if (tile_leader) {
-            int v;
-            do {
-              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            } while (v == 0);
+            for (int i = 1; i <= parts; ++i) {
+              const int* flag = p.sk_flags + (cta + i) * 2 + t;
+              int v;
+              do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+              } while (v == 0);
+            }
           }
           named_bar_sync(tile_bar, 256);
-          const float* slot = p.sk_ws + static_cast<size_t>(cta + 1) * SkSlot<kDP>::kFloats;
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(slot + SkSlot<kDP>::kOFloats +
-                                                                   (t * kTileM + r) * 2));
-          const float m_new = fmaxf(m_run, ml.x);
-          scale_mine = ex2_approx((m_run - m_new) * c);
-          scale_other = ex2_approx((ml.x - m_new) * c);
-          l_tot = l_tot * scale_mine + ml.y * scale_other;
-          m_run = m_new;
-          o_src = slot + (t * kTileM + r) * kDP + half * kOHalf;
+          float m_all = m_run;
+          for (int i = 1; i <= parts; ++i) {
+            const float* slot = p.sk_ws + static_cast<size_t>(cta + i) * SkSlot<kDP>::kFloats;
+            m_all = fmaxf(m_all, __ldcg(reinterpret_cast<const float2*>(slot + part_ml_off)).x);
+          }
+          f_mine = ex2_approx((m_run - m_all) * c);
+          l_tot *= f_mine;
+          for (int i = 1; i <= parts; ++i) {
+            const float* slot = p.sk_ws + static_cast<size_t>(cta + i) * SkSlot<kDP>::kFloats;
+            const float2 ml = __ldcg(reinterpret_cast<const float2*>(slot + part_ml_off));
+            l_tot = fmaf(ml.y, ex2_approx((ml.x - m_all) * c), l_tot);
+          }
+          m_run = m_all;
         }
         if (half == 0 && p.lse != nullptr && row < p.Nq)
           p.lse[static_cast<int64_t>(unit / p.sk_P) * p.Nq + row] = m_run * c + log2f(l_tot);
         const float inv_l = 1.f / l_tot;
-        const float f_mine = scale_mine * inv_l, f_other = scale_other * inv_l;
-        const int qb = kSkQDouble ? (seg & 1) : 0;
-        uint8_t* stage = smem + C::kQ + (qb * 2 + t) * C::kTileBytes;
+        f_mine *= inv_l;
+        // my turn on the staging tile: the previous user's TMA store has read it
+        if (use > 0) mbar_wait(bar_stage, (use - 1) & 1, 57);
+        uint8_t* stage = smem + C::kStage;
 #pragma unroll
         for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
           uint32_t o[32];
           tmem_ld_x32(tO + cidx * 32, o);
           tmem_wait_ld();
+          if (cidx == kOHalf / 32 - 1) {  // O_t has left TMEM: the next segment's first PV may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tile_free(t));
+          }
           float of[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) of[e] = __uint_as_float(o[e]) * f_mine;
           if (kind == 2) {
+            for (int i = 1; i <= parts; ++i) {
+              const float* slot = p.sk_ws + static_cast<size_t>(cta + i) * SkSlot<kDP>::kFloats;
+              const float f_i =
+                  ex2_approx((__ldcg(reinterpret_cast<const float2*>(slot + part_ml_off)).x - m_run) * c) * inv_l;
+              const float4* o_src = reinterpret_cast<const float4*>(slot + part_o_off) + cidx * 8 * 128;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 x = __ldcg(reinterpret_cast<const float4*>(o_src + cidx * 32 + e));
-              of[e] = fmaf(x.x, f_other, of[e]);
-              of[e + 1] = fmaf(x.y, f_other, of[e + 1]);
-              of[e + 2] = fmaf(x.z, f_other, of[e + 2]);
-              of[e + 3] = fmaf(x.w, f_other, of[e + 3]);
+              for (int e = 0; e < 32; e += 4) {
+                const float4 x = __ldcg(o_src + (e >> 2) * 128);
+                of[e] = fmaf(x.x, f_i, of[e]);
+                of[e + 1] = fmaf(x.y, f_i, of[e + 1]);
+                of[e + 2] = fmaf(x.z, f_i, of[e + 2]);
+                of[e + 3] = fmaf(x.w, f_i, of[e + 3]);
+              }
             }
           }
 #pragma unroll
@@ -454,26 +529,22 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
         }
         fence_proxy_async_smem();
-        tc_fence_before();
         named_bar_sync(tile_bar, 256);
         if (tile_leader) {
 #pragma unroll
           for (int db = 0; db < kDBlocks; ++db)
-            tma_store_4d(&tmap_o, sQ + (qb * 2 + t) * C::kTileBytes + db * 16384, db * 64, tile_row0,
-                         (unit / p.sk_P) % p.H, (unit / p.sk_P) / p.H);
+            tma_store_4d(&tmap_o, sStage + db * 16384, db * 64, tile_row0, hh, bb);
           tma_store_commit();
-          tma_store_wait_read();  // the Q_t buffer may be reloaded once the store has read it
-          if (kind == 2) {        // every thread of the tile has read the partial (barrier above)
-            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (cta + 1) * 2 + t),
-                         "r"(0)
+          tma_store_wait_read();  // the staging tile may be rewritten once the store has read it
+          mbar_arrive(bar_stage);
+          // every thread of the tile has read the partials (barrier above): lower the flags
+          for (int i = 1; i <= parts; ++i)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (cta + i) * 2 + t), "r"(0)
                          : "memory");
-          }
         }
         __syncwarp();
-        // warp 0 of the tile arrives after its leader's wait_read: Q_t / O_t are free for the next unit
-        if (lane == 0) mbar_arrive(bar_tile_free(t));
       }
-      seg_next(n);
+      wk.next();
     }
   }
 

@@ -40,13 +40,11 @@ struct Tc1Smem {
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kTileBytes;           // 2 stages
   static constexpr int kV = kK + 2 * kTileBytes;       // 2 stages
-  static constexpr int kP = kV + 2 * kTileBytes;       // P tile through smem (SS variant only)
-  static constexpr int kBars = kP + kTileM * kTileN * 2;
+  static constexpr int kBars = kV + 2 * kTileBytes;
   static constexpr int kTotal = kBars + 128 + 1024;    // + alignment slack
 };
 
-// kPsmem: route P through shared memory (SS MMA) instead of TMEM (TS MMA)
-template <int kDP, bool kBF16, bool kCausal, bool kPsmem>
+template <int kDP, bool kBF16, bool kCausal>
 __global__ void __launch_bounds__(128, 1)
 fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_k,
@@ -63,7 +61,6 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t sQ = smem_u32(smem + L::kQ);
   const uint32_t sK = smem_u32(smem + L::kK);
   const uint32_t sV = smem_u32(smem + L::kV);
-  const uint32_t sP = smem_u32(smem + L::kP);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBars + 64);
   const uint32_t bar_q = smem_u32(&bars[0]);
@@ -82,6 +79,12 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) {  // first tiles -> L2 before pdl_wait() (see fa_fwd_ws.cuh)
+      tma_prefetch_l2_4d(&tmap_q, db * 64, row0, h, b);
+      tma_prefetch_l2_4d(&tmap_k, db * 64, 0, h, b);
+      tma_prefetch_l2_4d(&tmap_v, db * 64, 0, h, b);
+    }
     mbar_init(bar_q, 1);
     mbar_init(bar_kv[0], 1);
     mbar_init(bar_kv[1], 1);
@@ -95,6 +98,9 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
@@ -199,26 +205,13 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
     }
 
-    // ---- P (16-bit) -> TMEM or smem
-    if constexpr (!kPsmem) {
+    // ---- P (16-bit) -> TMEM
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint32_t r[32];
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      uint32_t r[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = pack2<kBF16>(s[hlf * 64 + 2 * i], s[hlf * 64 + 2 * i + 1]);
-        tmem_st_x32(tmem + lane_base + kColP + hlf * 32, r);
-      }
-    } else {
-#pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        uint4 val;
-        val.x = pack2<kBF16>(s[ch * 8 + 0], s[ch * 8 + 1]);
-        val.y = pack2<kBF16>(s[ch * 8 + 2], s[ch * 8 + 3]);
-        val.z = pack2<kBF16>(s[ch * 8 + 4], s[ch * 8 + 5]);
-        val.w = pack2<kBF16>(s[ch * 8 + 6], s[ch * 8 + 7]);
-        *reinterpret_cast<uint4*>(smem + L::kP + sw128_offset_16bit(tid, ch * 8)) = val;
-      }
-      fence_proxy_async_smem();
+      for (int i = 0; i < 32; ++i) r[i] = pack2<kBF16>(s[hlf * 64 + 2 * i], s[hlf * 64 + 2 * i + 1]);
+      tmem_st_x32(tmem + lane_base + kColP + hlf * 32, r);
     }
     tmem_wait_st();
     tc_fence_before();
@@ -230,13 +223,7 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
       for (int k = 0; k < kTileN / 16; ++k) {
         const uint64_t b_desc =
             make_smem_desc_sw128(sV + stage * L::kTileBytes + k * 2048, 16384, 1024);
-        if constexpr (!kPsmem) {
-          umma_ts(tmem + kColO, tmem + kColP + k * 8, b_desc, idesc_o, (j > 0) || (k > 0));
-        } else {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(tmem + kColO, make_smem_desc_sw128(sP + off, 16, 1024), b_desc, idesc_o,
-                  (j > 0) || (k > 0));
-        }
+        umma_ts(tmem + kColO, tmem + kColP + k * 8, b_desc, idesc_o, (j > 0) || (k > 0));
       }
       tc_commit(bar_mma);
     }

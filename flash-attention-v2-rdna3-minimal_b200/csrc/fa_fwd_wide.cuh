@@ -115,6 +115,14 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
+    // Q, K0, K1, V0 -> L2 before pdl_wait() (see fa_fwd_ws.cuh)
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) {
+      tma_prefetch_l2_4d(&tmap_q, db * 64, row0, h, b);
+      tma_prefetch_l2_4d(&tmap_k, db * 64, 0, h, b);
+      tma_prefetch_l2_4d(&tmap_v, db * 64, 0, h, b);
+      if (n > 1) tma_prefetch_l2_4d(&tmap_k, db * 64, kTileN, h, b);
+    }
   }
   if (warp == 8) {
     tmem_alloc(smem_u32(tmem_slot), 512);
@@ -123,6 +131,9 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   if (*tmem_slot != 0u) __trap();  // one CTA per SM owns all of TMEM: constant addresses (see ws kernel)
   constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;

@@ -23,12 +23,6 @@
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 for padded head dims 192 and 256.
 #pragma once
 #include "fa_fwd_wide.cuh"
-#include "wide_softmax.cuh"
-
-// 1: software-pipelined softmax steps (wide_softmax.cuh) - measured slower, see there
-#ifndef FA_WIDE2_PIPELINED
-#define FA_WIDE2_PIPELINED 0
-#endif
 
 namespace fa {
 
@@ -138,6 +132,9 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   cluster_sync_all();  // both CTAs' barriers are initialised before anything arrives on them remotely
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   if (*tmem_slot != 0u) __trap();  // each CTA of the pair owns all of its SM's tensor memory
   constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;
@@ -265,55 +262,6 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_run = -INFINITY;
     float l_run = 0.f;
 
-#if FA_WIDE2_PIPELINED
-    // Software-pipelined steps (wide_softmax.cuh): the scores and the row maximum of tile j+1 are fetched
-    // during step j.  Two register arrays alternate between "current" and "next".
-    float sa[64], sb[64];
-    float mx_a = -INFINITY, mx_b = -INFINITY;
-    auto half_lim = [&](int j) {  // causal row limit of my half in tile j (<= 0: all hidden)
-      return r - (j - qtile) * kTileN + 1 - half * 64;
-    };
-    auto fetch = [&](float (&dst)[64], int j) {  // blocking: wait for S(j), load, mask, row maximum
-      return wide_fetch_tile(dst, tmem + lane_base + (j & 1) * 128 + half * 64, bar_s_full(j & 1), (j >> 1) & 1,
-                             j * kTileN + half * 64, p.Nkv, kCausal && j >= qtile, half_lim(j),
-                             my_max + (j & 1) * 256, other_max + (j & 1) * 256, pair_bar);
-    };
-    auto step = [&](float (&cur)[64], float (&nxt)[64], float mx_cur, float& mx_next, int j) {
-      const int buf = j & 1;
-      WideStepArgs a;
-      a.tS = tmem + lane_base + buf * 128 + half * 64;
-      a.tS_next = tmem + lane_base + (buf ^ 1) * 128 + half * 64;
-      a.tO = tO;
-      a.bar_early = p_early0 + buf * 8;
-      a.bar_mid = p_mid0 + buf * 8;
-      a.bar_late = p_late0 + buf * 8;
-      a.bar_s_next = bar_s_full(buf ^ 1);
-      a.s_next_parity = ((j + 1) >> 1) & 1;
-      a.bar_o = bar_o;
-      a.o_parity = static_cast<uint32_t>((j - 1) & 1);
-      a.has_next = j + 1 < n;
-      a.have_o = j > 0;
-      a.next_col0 = (j + 1) * kTileN + half * 64;
-      a.next_causal = kCausal && (j + 1 >= qtile);
-      a.next_r_lim_half = half_lim(j + 1);
-      a.Nkv = p.Nkv;
-      a.c = c;
-      a.my_max = my_max + ((j + 1) & 1) * 256;
-      a.other_max = other_max + ((j + 1) & 1) * 256;
-      a.pair_bar = pair_bar;
-      return wide_softmax_step<kDP, kBF16, true>(cur, nxt, mx_cur, mx_next, m_run, l_run, lane, a);
-    };
-    bool ready = false;  // tile j already fetched by the previous step?
-#pragma unroll 1
-    for (int j = 0; j < n; j += 2) {
-      if (!ready) mx_a = fetch(sa, j);
-      ready = step(sa, sb, mx_a, mx_b, j);
-      if (j + 1 < n) {
-        if (!ready) mx_b = fetch(sb, j + 1);
-        ready = step(sb, sa, mx_b, mx_a, j + 1);
-      }
-    }
-#else
 #pragma unroll 1
     for (int j = 0; j < n; ++j) {
       const int buf = j & 1;
@@ -332,7 +280,6 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                         p_early0 + buf * 8, p_late0 + buf * 8, 0u, p_mid0 + buf * 8, bar_o,
                                         static_cast<uint32_t>((j - 1) & 1));
     }
-#endif
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (my Q buffer) -> TMA store
     sFinal[half * 128 + r] = l_run;

@@ -337,6 +337,21 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
+    // the Q tiles and the first ring-full of K/V -> L2, before pdl_wait(): hides the HBM latency of the first
+    // loads under the previous kernel's tail (ptx.cuh: L2 is coherent, the loads themselves come after the wait)
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (n_t[t] > 0) tma_prefetch_l2_4d(&tmap_q, db * 64, row0 + t * kTileM, h, b);
+#pragma unroll
+      for (int j = 0; j < kS / 2; ++j) {
+        if (j < n_max) {
+          tma_prefetch_l2_4d(&tmap_k, db * 64, j * kTileN, h, b);
+          tma_prefetch_l2_4d(&tmap_v, db * 64, j * kTileN, h, b);
+        }
+      }
+    }
   }
   if (warp == 16) {
     tmem_alloc(smem_u32(tmem_slot), 512);
@@ -345,6 +360,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   // The CTA owns all 512 TMEM columns (one CTA per SM), so the allocation starts at lane 0,
   // column 0.  Using the literal 0 keeps every TMEM address a compile-time constant; otherwise
   // ptxas cannot prove the value read back from shared memory warp-uniform and wraps each

@@ -308,6 +308,9 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only below
+  pdl_wait();
+  pdl_launch_dependents();
   if (*tmem_slot != 0u) __trap();
   constexpr uint32_t tmem = 0u;
   const float c = p.scale_log2;

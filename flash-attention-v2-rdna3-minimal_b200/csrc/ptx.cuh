@@ -56,6 +56,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization
+// attribute may start while the previous kernel on the stream is still running; everything before
+// pdl_wait() (barrier init, TMEM allocation, descriptor + L2 prefetch) then overlaps that kernel's tail.
+// pdl_wait() returns once every prerequisite grid has completed and its memory operations are visible;
+// it is a no-op for a normally launched kernel.  pdl_launch_dependents() lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has issued it (or exited).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue two fp32 operations per instruction)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1,
@@ -227,6 +240,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// 4-D tiled prefetch global -> L2 (no shared-memory destination, no completion to wait for).  L2 is the
+// coherence point of global memory, so a prefetch issued before pdl_wait() can never make a later load
+// observe stale data; it only hides the HBM latency of the first tiles.
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 
 // 4-D tiled load global -> smem, completion on an mbarrier (complete_tx::bytes)

@@ -28,6 +28,7 @@ __all__ = [
     "FlashAttentionFunction",
     "flash_attn_forward",
     "flash_attn_forward_host",
+    "flash_attn_host_sync",
     "flash_attn_wmma",
 ]
 
@@ -171,11 +172,15 @@ def flash_attn_forward(q, k, v, causal=False, scale=None, BNHD_fmt=False, return
     return (o, lse) if return_lse else o
 
 
-def flash_attn_forward_host(q, k, v, causal=False, scale=None, out=None, return_lse=False):
+def flash_attn_forward_host(q, k, v, causal=False, scale=None, out=None, return_lse=False, wait=True):
     """Forward on HOST tensors (contiguous ``[B,H,N,D]``, ideally pinned): the C-ABI stages the
     inputs to the current CUDA device, runs the same kernels and copies the result back, overlapping
     the copies with compute.  Returns a host tensor (``out`` if given).  This is the end-to-end
-    path ``bench.py`` reports as ``e2e``."""
+    path ``bench.py`` reports as ``e2e``.
+
+    ``wait=False`` returns as soon as the work is enqueued (``fa_fwd_sm100_host_async``): the inputs and
+    the returned tensor must not be touched until ``flash_attn_host_sync()``; consecutive calls then
+    pipeline (the uploads of one call run under the tail of the previous one)."""
     for t in (q, k, v):
         if t.is_cuda or t.dim() != 4 or not t.is_contiguous():
             raise ValueError("flash_attn_forward_host expects contiguous 4-D host tensors")
@@ -192,13 +197,19 @@ def flash_attn_forward_host(q, k, v, causal=False, scale=None, out=None, return_
     elif out.shape != q.shape or out.dtype != q.dtype or out.is_cuda or not out.is_contiguous():
         raise ValueError("out must be a contiguous host tensor shaped and typed like q")
     lse = torch.empty((B, H, Nq), dtype=torch.float32, pin_memory=q.is_pinned()) if return_lse else None
-    rc = _capi.lib.fa_fwd_sm100_host(
+    entry = _capi.lib.fa_fwd_sm100_host if wait else _capi.lib.fa_fwd_sm100_host_async
+    rc = entry(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
         lse.data_ptr() if lse is not None else None,
         B, H, Nq, Nkv, D, _dtype_code(q.dtype), int(bool(causal)), float(scale),
     )
-    _capi.check(rc, "fa_fwd_sm100_host")
+    _capi.check(rc, "fa_fwd_sm100_host" if wait else "fa_fwd_sm100_host_async")
     return (out, lse) if return_lse else out
+
+
+def flash_attn_host_sync():
+    """Wait for every ``flash_attn_forward_host(..., wait=False)`` issued on the current device."""
+    _capi.check(_capi.lib.fa_host_sync(), "fa_host_sync")
 
 
 class _NativeModule:

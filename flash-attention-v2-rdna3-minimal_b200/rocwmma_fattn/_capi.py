@@ -14,44 +14,44 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # FA_FWD_SM100_LIB selects another build of the same C-ABI (e.g. the FA_TRACE debug library)
 LIB_PATH = os.environ.get("FA_FWD_SM100_LIB") or os.path.join(_PKG_ROOT, "lib", "libfa_fwd_sm100.so")
 
-FA_ABI_VERSION = 4
+FA_ABI_VERSION = 5
 FA_DTYPE_F16, FA_DTYPE_BF16 = 0, 1
 FA_OK, FA_ERR_INVALID_ARG, FA_ERR_UNSUPPORTED, FA_ERR_CUDA, FA_ERR_NO_DEVICE = 0, 1, 2, 3, 4
-FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_TC1_PSMEM, FA_KERNEL_WS, FA_KERNEL_SK = 0, 1, 2, 3, 4, 5
+FA_KERNEL_AUTO, FA_KERNEL_SIMT, FA_KERNEL_TC1, FA_KERNEL_WS, FA_KERNEL_SK = 0, 1, 2, 4, 5  # 3: retired
 FA_KERNEL_WIDE = 6
 FA_KERNEL_WS2 = 7
-FA_KERNEL_QUAD2 = 8
-FA_KERNEL_WS3 = 9
-FA_BWD_KERNEL_TC1, FA_BWD_KERNEL_WS = 1, 2
+FA_KERNEL_WS3 = 9  # 8: retired
 KERNEL_NAMES = {
     FA_KERNEL_AUTO: "auto",
     FA_KERNEL_SIMT: "simt",
     FA_KERNEL_TC1: "tc1",
-    FA_KERNEL_TC1_PSMEM: "tc1_psmem",
     FA_KERNEL_WS: "ws",
     FA_KERNEL_SK: "sk",
     FA_KERNEL_WIDE: "wide",
     FA_KERNEL_WS2: "ws2",
-    FA_KERNEL_QUAD2: "quad2",
     FA_KERNEL_WS3: "ws3",
 }
 
-# every symbol include/fa_fwd_sm100.h declares
+# every symbol include/fa_fwd_sm100.h (the boundary) and include/fa_fwd_sm100_test.h (test hooks) declare
 EXPORTED_SYMBOLS = (
     "fa_fwd_sm100",
     "fa_fwd_sm100_host",
+    "fa_fwd_sm100_host_async",
+    "fa_host_sync",
     "fa_bwd_sm100",
     "fa_host_workspace_release",
     "fa_last_error",
     "fa_abi_version",
     "fa_select_kernel",
-    "fa_set_kernel",
-    "fa_set_bwd_kernel",
     "fa_launch_count",
+    "fa_host_plan_chunks",
+)
+TEST_HOOK_SYMBOLS = (
+    "fa_set_kernel",
+    "fa_set_pdl",
+    "fa_set_wide_pairs",
     "fa_umma_selftest",
     "fa_umma2_selftest",
-    "fa_set_wide_pairs",
-    "fa_host_plan_chunks",
 )
 
 _I64x4 = ctypes.c_int64 * 4
@@ -65,10 +65,20 @@ def _load_build_module():
 
 
 def _open() -> ctypes.CDLL:
-    if not os.path.exists(LIB_PATH):
-        # same contract as the reference (build at import, FlashAttn.py:23-41), but ahead-of-time
-        # builds are preferred: `python __graft_entry__.py` / `python build.py`
-        _load_build_module().build()
+    if not os.environ.get("FA_FWD_SM100_LIB"):
+        # same contract as the reference (build at import, FlashAttn.py:23-41), but ahead-of-time builds are
+        # preferred: `python __graft_entry__.py` / `python build.py`.  A library that does not match the
+        # sources next to it (build.py keeps a source-hash stamp) is rebuilt when nvcc is here, and refused
+        # otherwise: kernel selectors and dispatch rules must agree with this module.
+        bm = _load_build_module()
+        if not bm.is_current():
+            if bm.have_nvcc():
+                bm.build()
+            elif not os.path.exists(LIB_PATH):
+                raise ImportError(f"{LIB_PATH} is missing and nvcc is not available to build it")
+            else:
+                raise ImportError(f"{LIB_PATH} is stale (csrc/ or include/ changed since it was built) and nvcc is "
+                                  "not available to rebuild it")
     lib = ctypes.CDLL(LIB_PATH)
     vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     p64 = ctypes.POINTER(ctypes.c_int64)
@@ -76,6 +86,10 @@ def _open() -> ctypes.CDLL:
     lib.fa_fwd_sm100.restype = i
     lib.fa_fwd_sm100_host.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f]
     lib.fa_fwd_sm100_host.restype = i
+    lib.fa_fwd_sm100_host_async.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, f]
+    lib.fa_fwd_sm100_host_async.restype = i
+    lib.fa_host_sync.argtypes = []
+    lib.fa_host_sync.restype = i
     lib.fa_bwd_sm100.argtypes = [vp] * 11 + [i] * 5 + [p64] * 8 + [i, i, f, vp]
     lib.fa_bwd_sm100.restype = i
     lib.fa_host_workspace_release.argtypes = []
@@ -88,8 +102,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_select_kernel.restype = i
     lib.fa_set_kernel.argtypes = [i]
     lib.fa_set_kernel.restype = i
-    lib.fa_set_bwd_kernel.argtypes = [i]
-    lib.fa_set_bwd_kernel.restype = i
+    lib.fa_set_pdl.argtypes = [i]
+    lib.fa_set_pdl.restype = i
     lib.fa_launch_count.argtypes = []
     lib.fa_launch_count.restype = ctypes.c_uint64
     lib.fa_umma_selftest.argtypes = [vp, vp, vp, i, i, ctypes.c_uint32, ctypes.c_uint32, vp]
@@ -164,11 +178,9 @@ def set_kernel(kernel: int) -> int:
     return prev
 
 
-def set_bwd_kernel(kernel: int) -> int:
-    prev = lib.fa_set_bwd_kernel(int(kernel))
-    if prev < 0:
-        raise ValueError(f"unknown backward kernel selector {kernel}")
-    return prev
+def set_pdl(enable: bool) -> bool:
+    """Programmatic dependent launch of the forward kernels on/off (test hook); returns the previous setting."""
+    return bool(lib.fa_set_pdl(int(bool(enable))))
 
 
 def select_kernel(B, H, Nq, Nkv, D, qs, ks, vs, os_, dtype, causal, scale) -> int:

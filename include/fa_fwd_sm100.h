@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FA_ABI_VERSION 4
+#define FA_ABI_VERSION 5
 
 /* element types (reference: host.cpp:32-44 dispatches on torch::kFloat16 / torch::kBFloat16) */
 #define FA_DTYPE_F16 0
@@ -49,22 +49,20 @@ extern "C" {
 #define FA_KERNEL_AUTO 0
 #define FA_KERNEL_SIMT 1       /* CUDA-core kernel, any head dim <= 1024 */
 #define FA_KERNEL_TC1 2        /* tcgen05, one 128-row Q tile per CTA, P through TMEM */
-#define FA_KERNEL_TC1_PSMEM 3  /* as TC1 but P through shared memory */
+/* 3 was FA_KERNEL_TC1_PSMEM (P through shared memory): removed in ABI 5, the value stays reserved */
 #define FA_KERNEL_WS 4         /* tcgen05, warp-specialised, two Q tiles per CTA (the fast path) */
 #define FA_KERNEL_SK 5         /* FA_KERNEL_WS made persistent: one CTA per SM, work split evenly over
-                                  (query block, KV tile) items; non-causal, Nq % 256 == 0, >= 1 query
-                                  block per SM; falls back to FA_KERNEL_WS otherwise */
+                                  (query block, KV tile) items, a query block shared by any number of
+                                  CTAs; non-causal, Nq % 256 == 0; falls back to FA_KERNEL_WS otherwise */
 #define FA_KERNEL_WIDE 6       /* tcgen05, one Q tile per CTA with the score tile double-buffered: head dims
                                   129..256 (on CTA pairs above 192), and small or short-causal problems at head
                                   dims <= 128 */
 #define FA_KERNEL_WS2 7        /* FA_KERNEL_WS on CTA pairs (cluster of two, cta_group::2): each SM fetches half of
                                   every K/V tile; non-causal (causal requests run FA_KERNEL_WS) */
-#define FA_KERNEL_QUAD2 8      /* one Q tile per CTA on CTA pairs, double-buffered S, FOUR threads per query row
-                                  (16 softmax warps on the one tile); head dims <= 128 */
-#define FA_KERNEL_WS3 9        /* FA_KERNEL_WS2 with P outside the S columns, so that S_t(j+1) is issued ahead of
-                                  O_t += P_t(j) V: in spare tensor memory at head dims <= 64 (the default there for
-                                  all but small or short-KV problems), through shared memory at head dim 128 (measured
-                                  slower, never automatic) */
+/* 8 was FA_KERNEL_QUAD2 (four threads per query row, measured slower): removed in ABI 5, reserved */
+#define FA_KERNEL_WS3 9        /* FA_KERNEL_WS2 with P in spare tensor memory, so that S_t(j+1) is issued ahead of
+                                  O_t += P_t(j) V: head dims <= 64 (the default there for all but small or short-KV
+                                  problems); a request at head dims 65..128 runs FA_KERNEL_WS */
 
 /*
  * Attention forward on device buffers.  Replaces host.cpp:30-45 `forward` + kernel_*.cu
@@ -98,6 +96,19 @@ int fa_fwd_sm100(const void* q, const void* k, const void* v, void* o, float* ls
  */
 int fa_fwd_sm100_host(const void* q, const void* k, const void* v, void* o, float* lse, int B,
                       int H, int Nq, int Nkv, int D, int dtype, int causal, float scale);
+
+/*
+ * fa_fwd_sm100_host() without the final wait: returns once the copies and kernels are enqueued.  `q`, `k`,
+ * `v`, `o` (and `lse`) must stay valid and untouched until fa_host_sync() returns.  Consecutive calls on a
+ * device pipeline through two staging sets: the host->device copies of call i+1 run under the last kernel
+ * and the device->host copy of call i, so a sequence of calls costs the PCIe time of its bytes plus one tail
+ * instead of one tail per call.  An error drains everything in flight before it is returned.
+ */
+int fa_fwd_sm100_host_async(const void* q, const void* k, const void* v, void* o, float* lse, int B,
+                            int H, int Nq, int Nkv, int D, int dtype, int causal, float scale);
+
+/* Wait until every fa_fwd_sm100_host_async() call issued on the current device has delivered its output. */
+int fa_host_sync(void);
 
 /*
  * Attention backward on device buffers.  Replaces host.cpp:47-58 `backward` + kernel_*.cu
@@ -134,7 +145,15 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
  */
 int fa_host_plan_chunks(int B, int H, int Nq, int Nkv, int D, int causal, int* out, int cap);
 
-/* Release the device workspace and streams fa_fwd_sm100_host() caches for the current device. */
+/* Release what the library caches on the current device: the staging buffers and streams of the host-buffer
+ * path and the persistent kernel's per-stream workspaces.  Call it only when no launch of this library is in
+ * flight and no CUDA graph that captured one will be replayed again.
+ *
+ * Workspace rule for FA_KERNEL_SK: partial results of query blocks shared by several CTAs go through a
+ * workspace owned by the (device, stream) the launch was issued - or captured - on.  Launches on one stream
+ * are ordered, so they share it safely; a graph captured on stream S must not be replayed concurrently with
+ * other work of this library issued on S or with another graph captured on S (replay such graphs on S, or
+ * capture each on its own stream).  A capture on a stream that has no workspace yet uses FA_KERNEL_WS. */
 int fa_host_workspace_release(void);
 
 /* Message describing the last error on the calling thread ("" if none). */
@@ -142,19 +161,6 @@ const char* fa_last_error(void);
 
 /* FA_ABI_VERSION the library was built with. */
 int fa_abi_version(void);
-
-/* FA_KERNEL_WIDE at head dims 193..256 runs on CTA pairs (thread-block cluster of two,
- * tcgen05 cta_group::2: each SM fetches half of every K/V tile) unless disabled here (test / benchmarking
- * hook).  Returns the previous setting. */
-int fa_set_wide_pairs(int enable);
-
-/* backward kernel selectors for fa_set_bwd_kernel() */
-#define FA_BWD_KERNEL_TC1 1    /* P and dS through shared memory (csrc/fa_bwd_tc.cuh); the default */
-#define FA_BWD_KERNEL_WS 2     /* warp-specialised, transposed scores, P^T / dS^T from TMEM (csrc/fa_bwd_ws.cuh) */
-
-/* Choose the backward kernel for subsequent fa_bwd_sm100() calls in this process (test /
- * benchmarking hook).  Returns the previous setting or a negative error code. */
-int fa_set_bwd_kernel(int kernel);
 
 /*
  * Which kernel fa_fwd_sm100() would run for this problem (one of FA_KERNEL_*, never AUTO), or a
@@ -164,31 +170,8 @@ int fa_select_kernel(int B, int H, int Nq, int Nkv, int D, const int64_t q_strid
                      const int64_t k_strides[4], const int64_t v_strides[4],
                      const int64_t o_strides[4], int dtype, int causal, float scale);
 
-/* Force a kernel (FA_KERNEL_*) for subsequent calls in this process; FA_KERNEL_AUTO restores the
- * heuristic.  Test / benchmarking hook.  Returns the previous setting. */
-int fa_set_kernel(int kernel);
-
 /* Number of kernel launches issued by this library in this process (all threads). */
 uint64_t fa_launch_count(void);
-
-/*
- * UMMA / TMA / TMEM self-test: computes one 128x128x128 product through the same operand paths the
- * attention kernels use (mode 0: A.B^T both K-major; 1: A.B with B MN-major; 2: A from TMEM;
- * 3: A written to smem by threads; 4: A^T.B with A and B MN-major, the backward's dV/dK products).
- * a, b: device [128,128] 16-bit row-major; out: device
- * [128,128] fp32.  lbo/sbo: B-descriptor byte offsets for modes 1-3 (0,0 = the values the kernels
- * use).  Counterpart of the reference's gemm_test/ micro-kernels.
- */
-int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mode, uint32_t lbo,
-                     uint32_t sbo, void* stream);
-
-/*
- * CTA-pair (cluster of 2, tcgen05 cta_group::2) plumbing probe: out[256,128] (fp32) = A[256,128] * B with
- * every operand 16-bit, each CTA of the pair holding its own 128 rows of A / out and half of B.
- *   mode 0  A from shared memory (K-major); b = B as [n=128][k=128] row-major, CTA r takes rows 64r..64r+63
- *   mode 1  A from tensor memory;           b = B as [k=128][n=128] row-major, CTA r takes columns 64r..64r+63
- */
-int fa_umma2_selftest(const void* a, const void* b, float* out, int dtype, int mode, void* stream);
 
 #ifdef __cplusplus
 }

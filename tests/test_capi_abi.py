@@ -1,6 +1,6 @@
 """CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
-include/fa_fwd_sm100.h declares, validates arguments, and fails loudly (never falls back) when no
-sm_100 device is present.  No compute is launched here."""
+include/fa_fwd_sm100.h (the boundary) and include/fa_fwd_sm100_test.h (test hooks) declare, validates
+arguments, and fails loudly (never falls back) when no sm_100 device is present.  No compute is launched here."""
 import ctypes
 import os
 import re
@@ -12,24 +12,34 @@ from rocwmma_fattn import _capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "fa_fwd_sm100.h")
+TEST_HEADER = os.path.join(ROOT, "include", "fa_fwd_sm100_test.h")
 
 
-def _declared_functions():
-    src = open(HEADER).read()
+def _declared_functions(path):
+    src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_all_exported():
-    names = _declared_functions()
+    names = _declared_functions(HEADER)
     assert len(names) >= 9
     for n in names:
         assert hasattr(_capi.lib, n), f"{n} declared in include/fa_fwd_sm100.h but not exported"
     assert sorted(_capi.EXPORTED_SYMBOLS) == names
+    # the boundary header carries no test hooks: they live in their own header
+    assert not [n for n in names if n.startswith("fa_set_") or n.endswith("_selftest")]
+
+
+def test_test_hook_header_symbols_all_exported():
+    names = _declared_functions(TEST_HEADER)
+    for n in names:
+        assert hasattr(_capi.lib, n), f"{n} declared in include/fa_fwd_sm100_test.h but not exported"
+    assert sorted(_capi.TEST_HOOK_SYMBOLS) == names
 
 
 def test_abi_version_and_error_string():
-    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 4
+    assert _capi.lib.fa_abi_version() == _capi.FA_ABI_VERSION == 5
     assert isinstance(_capi.last_error(), str)
 
 
@@ -157,5 +167,8 @@ def test_set_kernel_roundtrip():
         assert _capi.set_kernel(_capi.FA_KERNEL_AUTO) == _capi.FA_KERNEL_SIMT
         with pytest.raises(ValueError):
             _capi.set_kernel(99)
+        for retired in (3, 8):  # FA_KERNEL_TC1_PSMEM / FA_KERNEL_QUAD2 (ABI 4)
+            with pytest.raises(ValueError):
+                _capi.set_kernel(retired)
     finally:
         _capi.set_kernel(prev)

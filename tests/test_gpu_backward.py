@@ -22,20 +22,6 @@ DEV = "cuda"
 F16, BF16 = torch.float16, torch.bfloat16
 
 
-BWD_KERNELS = {"ws": _capi.FA_BWD_KERNEL_WS, "tc1": _capi.FA_BWD_KERNEL_TC1}
-
-
-class forced_bwd_kernel:
-    def __init__(self, name):
-        self.sel = BWD_KERNELS[name]
-
-    def __enter__(self):
-        self.prev = _capi.set_bwd_kernel(self.sel)
-
-    def __exit__(self, *exc):
-        _capi.set_bwd_kernel(self.prev)
-
-
 def grads(q, k, v, d_o, causal=False, scale=None, bnhd=False):
     q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
     o = FlashAttentionFunction.apply(q, k, v, None, causal, scale, bnhd)
@@ -60,16 +46,14 @@ def truth(q, k, v, d_o, causal=False, scale=None):
             orc.sdpa_backward(q, k, v, d_o, causal=causal, scale=scale, dtype=q.dtype))
 
 
-@pytest.mark.parametrize("kernel", ["ws", "tc1"])
 @pytest.mark.parametrize("bnhd", [False, True])
 @pytest.mark.parametrize("name", golden_bwd_names())
-def test_backward_golden_vectors(name, bnhd, kernel):
+def test_backward_golden_vectors(name, bnhd):
     g = load_golden_bwd(name)
     q, k, v, d_o = (g[x].to(DEV) for x in ("q", "k", "v", "d_o"))
     if bnhd:
         q, k, v, d_o = (t.transpose(1, 2).contiguous() for t in (q, k, v, d_o))
-    with forced_bwd_kernel(kernel):
-        _, dq, dk, dv = grads(q, k, v, d_o, g["causal"], None, bnhd)
+    _, dq, dk, dv = grads(q, k, v, d_o, g["causal"], None, bnhd)
     if bnhd:
         dq, dk, dv = (t.transpose(1, 2) for t in (dq, dk, dv))
     ref = (g["dq_f32"], g["dk_f32"], g["dv_f32"])
@@ -95,23 +79,21 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["ws", "tc1"])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("dtype", [F16, BF16])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_backward_matches_fp32_autograd(shape, dtype, causal, kernel):
+def test_backward_matches_fp32_autograd(shape, dtype, causal):
     B, H, Nq, Nkv, D = shape
     q, k, v = orc.make_inputs(B, H, Nq, Nkv, D, dtype, seed=sum(shape) + 7 * int(causal))
     g = torch.Generator().manual_seed(99 + sum(shape))
     d_o = torch.rand((B, H, Nq, D), generator=g).to(dtype)
     ref, b16 = truth(q, k, v, d_o, causal)
-    with forced_bwd_kernel(kernel):
-        _, dq, dk, dv = grads(q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV), causal)
+    _, dq, dk, dv = grads(q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV), causal)
     # a single key: softmax is identically 1, the exact dQ and dK are 0 and plain PyTorch returns
     # exactly 0, so the relative gate degenerates; what remains is (dP - rowsum(dO o O16)) summed over
     # the query rows, i.e. the 16-bit rounding of the stored O (any FA2 backward has it)
     atol = 2e-4 if Nkv == 1 else 0.0
-    assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal} {kernel}", atol)
+    assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal}", atol)
 
 
 def test_backward_randn_inputs_and_custom_scale():

@@ -18,7 +18,7 @@ import torch
 from rocwmma_fattn import _capi
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
 if os.environ.get("FA_KERNEL"):
-    _capi.set_kernel({"ws": _capi.FA_KERNEL_WS, "sk": _capi.FA_KERNEL_SK, "ws2": _capi.FA_KERNEL_WS2, "quad2": _capi.FA_KERNEL_QUAD2, "ws3": _capi.FA_KERNEL_WS3,
+    _capi.set_kernel({"ws": _capi.FA_KERNEL_WS, "sk": _capi.FA_KERNEL_SK, "ws2": _capi.FA_KERNEL_WS2, "ws3": _capi.FA_KERNEL_WS3,
                       "wide": _capi.FA_KERNEL_WIDE}[os.environ["FA_KERNEL"]])
 ns = [int(x) for x in os.environ["FA_NS"].split(",")]
 causal = os.environ.get("FA_CAUSAL", "0") == "1"

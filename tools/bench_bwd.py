@@ -14,8 +14,6 @@ import torch
 from rocwmma_fattn import _capi
 from rocwmma_fattn.FlashAttn import flash_attn_wmma
 
-_capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_WS if os.environ.get("FA_BWD", "tc1") == "ws"
-                     else _capi.FA_BWD_KERNEL_TC1)
 
 ns = [int(x) for x in sys.argv[1:]] or [1024, 4096, 16384]
 H, D = 16, 128

@@ -10,8 +10,6 @@ from rocwmma_fattn.FlashAttn import flash_attn_wmma
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 causal = len(sys.argv) > 2 and sys.argv[2] == "causal"
-if len(sys.argv) > 3 and sys.argv[3] == "tc1":
-    _capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_TC1)
 D, H = 128, 16
 torch.manual_seed(0)
 q, k, v, d_o = (torch.rand(1, H, N, D, dtype=torch.float16, device="cuda") for _ in range(4))

@@ -4,7 +4,7 @@ import torch
 from rocwmma_fattn import _capi
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
 torch.manual_seed(0)
-for name in ("ws3", "quad2", "ws2"):
+for name in ("ws3", "ws2", "sk"):
     _capi.set_kernel({v: k for k, v in _capi.KERNEL_NAMES.items()}[name])
     for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 768, 640, 128, torch.float16, False), (1, 1, 300, 900, 64, torch.bfloat16, False),
                                           (1, 1, 640, 640, 128, torch.bfloat16, True)]:
