@@ -24,6 +24,7 @@
 
 #include "../../include/fa_fwd_sm100.h"
 #include "../../include/fa_fwd_sm100_test.h"
+#include "fa_bwd_simt.cuh"
 #include "fa_bwd_tc.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
@@ -204,11 +205,11 @@ int choose_kernel_shape(const Problem& p) {
   // and a shorter iteration (graph-timed, fp16 H=16 D=128: N=512 252 vs 179 TFLOPS, N=1024 654 vs 460;
   // at N=2048 - 256 tiles, two rounds - the two-tile kernel is back in front, 1081 vs 875).
   if (static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM) <= 148) return FA_KERNEL_WIDE;
-  // Long non-causal problems with many rounds: the two-tile kernel on CTA pairs (each SM fetches half of
-  // every K/V tile).  A/B on one box, fp16 H=16 D=128 N=16384: 1457-1461 vs 1441-1446 TFLOPS burst, 1250-1253 vs
-  // 1239-1241 sustained (+1 %); at N=4096 the lock step of the pair costs 3.6 %, so short KV loops stay put.
-  static const bool no_ws2 = std::getenv("FA_NO_WS2") != nullptr;  // A/B switch for whole-bench comparisons
-  if (!no_ws2 && !p.causal && p.Nkv >= 8192 &&
+  // (The two-tile kernel on CTA pairs, FA_KERNEL_WS2, was +1 % at N=16384 in round 1; with PDL and the L2
+  // prefetch in the one-shot kernel it measures 2 % behind - 1590 vs 1556 us, profiles/r02_sweep_kernels.json -
+  // so it is no longer selected automatically.  FA_WS2=1 in the environment restores the round-1 rule.)
+  static const bool use_ws2 = std::getenv("FA_WS2") != nullptr;
+  if (use_ws2 && !p.causal && p.Nkv >= 8192 &&
       static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) >= 4 * 148)
     return FA_KERNEL_WS2;
   return FA_KERNEL_WS;
@@ -409,24 +410,27 @@ void release_sk_workspaces(int device) {
 // What the persistent kernel can run at all: non-causal, whole 256-row query blocks.
 bool sk_possible(const Problem& p) { return !p.causal && p.Nq % (2 * fa::kTileM) == 0; }
 
-// Cost model for head dims <= 128, in units of one "step" = the time the two-tile
-// kernels need for one KV tile of a 256-row query block (~1.9 us at the sustained clock):
-//   one-shot, two tiles per CTA (ws)   rounds of U CTAs on n_sm SMs, each T steps + a fixed cost per CTA
-//   persistent (sk)                    ceil(U T / n_sm) steps + a cost per unit boundary + the fixed cost once
-//   one tile per CTA (wide)            rounds of U128 CTAs, each T shorter steps + a (smaller) fixed cost
-// The constants are fitted to the round-2 A/B runs (tools/ab_bench.py, profiles/r02_ab_*.json).
+// Cost model for the persistent kernel against the one-shot two-tile kernel, in units of one
+// "step" = the time the two-tile kernels need for one KV tile of a 256-row query block (~1.7 us):
+//   one-shot (ws)    ceil(U / n_sm) rounds of T steps, ~2 steps of fixed cost per CTA (launch, prologue, first
+//                    loads, first softmax, epilogue, drain)
+//   persistent (sk)  ceil(U T / n_sm) steps, ~1 step per unit boundary inside a CTA (pipelined: round-2 A/B on
+//                    whole units, 592 units on 148 SMs: 232 vs 236 us), ~8 steps when units are split between
+//                    CTAs (the partial round trip through L2 and the merge at the end of the range: round-2
+//                    timeline, tools/trace_sk.py), ~2 steps of fixed cost once
+// Fitted to profiles/r02_sweep_kernels.json (fp16 H=16 D=128, sk vs ws in us): N=2048 38.4 / 31.2, 4096 110.7 /
+// 112.1, 8192 397 / 431, 16384 1538 / 1545.
 struct KernelCosts {
-  double ws, sk, wide;
+  double ws, sk;
 };
 KernelCosts estimate_costs(const Problem& p, int n_sm) {
-  const double T = static_cast<double>((p.Nkv + fa::kTileN - 1) / fa::kTileN) * (p.causal ? 0.5 : 1.0);
+  const double T = static_cast<double>((p.Nkv + fa::kTileN - 1) / fa::kTileN);
   const long long U = static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM));
-  const long long U128 = static_cast<long long>(p.B) * p.H * ((p.Nq + fa::kTileM - 1) / fa::kTileM);
   KernelCosts k;
-  k.ws = static_cast<double>((U + n_sm - 1) / n_sm) * (T + 2.6);
+  k.ws = static_cast<double>((U + n_sm - 1) / n_sm) * (T + 2.0);
   const double per_cta = std::ceil(static_cast<double>(U) * T / n_sm);
-  k.sk = per_cta + 0.8 * (std::ceil(per_cta / T) + 1.0) + 2.6;
-  k.wide = static_cast<double>((U128 + n_sm - 1) / n_sm) * (0.72 * T + 2.2);
+  const bool split = (U % n_sm) != 0;
+  k.sk = per_cta + 1.0 * std::ceil(per_cta / T) + (split ? 8.0 : 0.0) + 2.0;
   return k;
 }
 
@@ -435,7 +439,7 @@ bool sk_eligible(const Problem& p, int n_sm) {
   if (!sk_possible(p) || n_sm <= 0) return false;
   if (p.Nkv < 4 * fa::kTileN) return false;  // units of a tile or two: nothing to split, only boundaries to pay for
   const KernelCosts k = estimate_costs(p, n_sm);
-  return k.sk < 0.97 * k.ws && k.sk < 0.97 * k.wide;
+  return k.sk < 0.985 * k.ws;
 }
 
 template <int kDP, bool kBF16>
@@ -1165,27 +1169,56 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
                   tma_ok_strides(p.vs) && tma_ok_strides(dos) && tma_ok_strides(dks) &&
                   tma_ok_strides(dvs) && aligned16(q) && aligned16(k) && aligned16(v) &&
                   aligned16(d_o) && aligned16(dk) && aligned16(dv) && aligned16(dq_accum);
-  if (!tc)
-    return fail(FA_ERR_UNSUPPORTED,
-                "fa_bwd_sm100 needs head dim % 8 == 0 and <= 128 with 16-byte aligned pointers and "
-                "strides (pad the head dim in the caller, as FlashAttn.py does)");
+  if (!tc && D > fa::kSimtMaxD) return fail(FA_ERR_UNSUPPORTED, "head dim > 1024 is not supported");
   int dev;
   if ((rc = check_device(&dev))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const int64_t rows = int64_t(B) * H * Nq;
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  // 1. delta = rowsum(dO o O), dq_accum = 0
+  // 1. delta = rowsum(dO o O), dq_accum = 0 (the generic path does not use the accumulator)
+  const int acc_ld = tc ? D : 0;
   if (dtype == FA_DTYPE_BF16)
     fa::fa_bwd_delta_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta, dq_accum,
-        B, H, Nq, D, D, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
+        B, H, Nq, D, acc_ld, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
   else
     fa::fa_bwd_delta_kernel<__half><<<blocks, 256, 0, st>>>(
         static_cast<const __half*>(o), static_cast<const __half*>(d_o), delta, dq_accum, B, H, Nq, D,
-        D, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
+        acc_ld, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+
+  if (!tc) {
+    // generic CUDA-core path (fa_bwd_simt.cuh): head dims 129..1024, head dims not a multiple of 8,
+    // unaligned pointers or strides - everything the forward's generic kernel accepts
+    fa::SimtBwdParams sp;
+    sp.q = q; sp.k = k; sp.v = v; sp.d_o = d_o; sp.dq = dq; sp.dk = dk; sp.dv = dv;
+    sp.lse = lse; sp.delta = delta;
+    sp.B = B; sp.H = H; sp.Nq = Nq; sp.Nkv = Nkv; sp.D = D;
+    memcpy(sp.qs, p.qs, sizeof sp.qs);
+    memcpy(sp.ks, p.ks, sizeof sp.ks);
+    memcpy(sp.vs, p.vs, sizeof sp.vs);
+    memcpy(sp.dos, dos, sizeof dos);
+    memcpy(sp.dqs, dqs, sizeof dqs);
+    memcpy(sp.dks, dks, sizeof dks);
+    memcpy(sp.dvs, dvs, sizeof dvs);
+    sp.causal = causal;
+    sp.scale = scale;
+    sp.scale_log2 = scale * 1.4426950408889634f;
+    const int smem = fa::kSimtWarps * 2 * D * static_cast<int>(sizeof(float));
+    dim3 gq((Nq + fa::kSimtWarps - 1) / fa::kSimtWarps, H, B), gk((Nkv + fa::kSimtWarps - 1) / fa::kSimtWarps, H, B);
+    if (dtype == FA_DTYPE_BF16) {
+      fa::fa_bwd_simt_dq_kernel<__nv_bfloat16><<<gq, fa::kSimtWarps * 32, smem, st>>>(sp);
+      fa::fa_bwd_simt_dkv_kernel<__nv_bfloat16><<<gk, fa::kSimtWarps * 32, smem, st>>>(sp);
+    } else {
+      fa::fa_bwd_simt_dq_kernel<__half><<<gq, fa::kSimtWarps * 32, smem, st>>>(sp);
+      fa::fa_bwd_simt_dkv_kernel<__half><<<gk, fa::kSimtWarps * 32, smem, st>>>(sp);
+    }
+    FA_CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return FA_OK;
+  }
 
   // 2. main kernel
   BwdMaps m;

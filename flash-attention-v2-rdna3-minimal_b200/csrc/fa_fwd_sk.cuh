@@ -36,6 +36,18 @@
 
 namespace fa {
 
+// Debug-only timeline (-DFA_TRACE): the leader thread of tile 0 stamps globaltimer into p.trace[cta * 32 + slot]:
+// slot 0 = start, then per segment 1 + 3 seg = KV loop done, 2 + 3 seg = partials awaited, 3 + 3 seg = epilogue done
+// (tools/trace_sk.py)
+#ifdef FA_TRACE
+#define FA_SK_TR(slot)                                                                                   \
+  do {                                                                                                   \
+    if (p.trace != nullptr && tile_leader && t == 0 && (slot) < 32) p.trace[cta * 32 + (slot)] = globaltimer_ns(); \
+  } while (0)
+#else
+#define FA_SK_TR(slot) do { } while (0)
+#endif
+
 // workspace slot of one CTA: unnormalised O of both tiles (fp32, [tile][half][kDP/8 float4s][128 rows]),
 // then (m, l) per row
 template <int kDP>
@@ -56,7 +68,7 @@ struct SkCfg {
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kStage = kKV + kStages * kTileBytes;  // O staging
   static constexpr int kBars = kStage + kTileBytes;
-  static constexpr int kNumBars = 17 + 2 * kStages;
+  static constexpr int kNumBars = 22 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;  // float [2 tile][2 half][128]; also row sums
   static constexpr int kTotal = kMax + 2 * 2 * 128 * 4;
   static_assert(kTotal <= 232448, "shared memory budget");
@@ -65,11 +77,9 @@ struct SkCfg {
 // Segment walker: the same sequence in every role.  First `dp` whole units in round-robin order, then the
 // stream-K range of this CTA over the remaining units.
 struct SkWalker {
-  int dp, round, u, t0, rem, cta, G, T;
-  __device__ __forceinline__ void init(const TcParams& p, int cta_, int G_) {
-    cta = cta_;
-    G = G_;
-    T = p.sk_T;
+  int dp, round, u, t0, rem;  // (CTA index, grid size and tiles per unit are passed in: they cost no registers)
+  __device__ __forceinline__ void init(const TcParams& p, int cta, int G) {
+    const int T = p.sk_T;
     dp = p.sk_dp;
     round = 0;
     const long long pos_begin = p.sk_W * cta / G;
@@ -80,10 +90,10 @@ struct SkWalker {
     rem = static_cast<int>(pos_end - pos_begin);
   }
   __device__ __forceinline__ bool more() const { return dp > 0 || rem > 0; }
-  __device__ __forceinline__ int unit() const { return dp > 0 ? round * G + cta : u; }
+  __device__ __forceinline__ int unit(int cta, int G) const { return dp > 0 ? round * G + cta : u; }
   __device__ __forceinline__ int first() const { return dp > 0 ? 0 : t0; }
-  __device__ __forceinline__ int count() const { return dp > 0 ? T : min(T - t0, rem); }
-  __device__ __forceinline__ void next() {
+  __device__ __forceinline__ int count(int T) const { return dp > 0 ? T : min(T - t0, rem); }
+  __device__ __forceinline__ void next(int T) {
     if (dp > 0) {
       --dp;
       ++round;
@@ -94,6 +104,15 @@ struct SkWalker {
     }
   }
 };
+
+// A zero the compiler cannot see through: values computed from it are computed AFTER this point in program
+// order (volatile asm is not moved across the volatile asm of the KV loop), i.e. they are not kept live in
+// registers across the loop, where the 64 scores of the softmax step need every register there is.
+__device__ __forceinline__ int opaque_zero() {
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+}
 
 template <int kDP, bool kBF16>
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -133,10 +152,18 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_p_mid = [&](int t) { return smem_u32(&bars[12 + t]); };       // 8 softmax warps; per item
   // tcgen05.commit behind the last S_t product of a segment: the Q_t buffer may be reloaded; per segment
   auto bar_q_free = [&](int t) { return smem_u32(&bars[14 + t]); };
-  // count 1: the O staging tile is free again; one phase per use, uses numbered 2 * segment + tile
-  const uint32_t bar_stage = smem_u32(&bars[16]);
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[17 + s]); };     // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[17 + kS + s]); };  // tcgen05.commit
+  // The O staging tile is used in turns, numbered k = 2 * (final segments so far) + tile (producer parts
+  // do not use it): the 8 softmax warps of the tile fill it and arrive on bar_stage_full (phase k); the store
+  // warp (warp 18) issues the TMA store, waits until it has read the tile and arrives on bar_stage_free.
+  const uint32_t bar_stage_full = smem_u32(&bars[16]);                   // 8 softmax warps
+  const uint32_t bar_stage_free = smem_u32(&bars[17]);                   // count 1
+  // producer part (at most one per CTA): the 8 softmax warps of tile t have stored their partial; the store
+  // warp then publishes it (flag, release at gpu scope) while the softmax warps move on
+  auto bar_part_done = [&](int t) { return smem_u32(&bars[18 + t]); };   // 8 softmax warps, one phase
+  // consumer part (at most one per CTA): the store warp has seen the flags of every producer part of tile t
+  auto bar_parts_ready = [&](int t) { return smem_u32(&bars[20 + t]); };  // count 1, one phase
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[22 + s]); };     // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[22 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -163,8 +190,11 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_tile_free(t), 8);
       mbar_init(bar_p_mid(t), 8);
       mbar_init(bar_q_free(t), 1);
+      mbar_init(bar_part_done(t), 8);
+      mbar_init(bar_parts_ready(t), 1);
     }
-    mbar_init(bar_stage, 1);
+    mbar_init(bar_stage_full, 8);
+    mbar_init(bar_stage_free, 1);
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
       mbar_init(bar_kv_full(s), 1);
@@ -179,8 +209,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     tma_prefetch_desc(&tmap_o);
     if (wk.more()) {  // first segment's Q tiles and first ring-full of K/V -> L2 before pdl_wait() (fa_fwd_ws.cuh)
       int row0, hh, bb;
-      unit_coords(wk.unit(), row0, hh, bb);
-      const int t0 = wk.first(), n = wk.count();
+      unit_coords(wk.unit(cta, G), row0, hh, bb);
+      const int t0 = wk.first(), n = wk.count(T);
 #pragma unroll
       for (int db = 0; db < kDBlocks; ++db) {
         tma_prefetch_l2_4d(&tmap_q, db * 64, row0, hh, bb);
@@ -218,11 +248,24 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // =======================================================================================
       if (elect_one()) {
         int kvi = 0;  // running K/V ring index (K and V alternate)
+        auto load_kv = [&](int x, int t0, int hh, int bb) {  // element x of a segment's K V K V ... sequence
+          const int slot = kvi % kS;
+          const uint32_t use = kvi / kS;
+          mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
+          mbar_arrive_expect_tx(bar_kv_full(slot), C::kTileBytes);
+          const CUtensorMap* map = (x & 1) ? &tmap_v : &tmap_k;
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db)
+            tma_load_4d(sKV + slot * C::kTileBytes + db * 16384, map, bar_kv_full(slot), db * 64,
+                        (t0 + (x >> 1)) * kTileN, hh, bb);
+          ++kvi;
+        };
+        bool k0_loaded = false;  // the first K tile of this segment went out behind the previous segment's tiles
         for (int seg = 0; wk.more(); ++seg) {
-          const int n = wk.count();
+          const int n = wk.count(T);
           const int t0 = wk.first();
           int row0, hh, bb;
-          unit_coords(wk.unit(), row0, hh, bb);
+          unit_coords(wk.unit(cta, G), row0, hh, bb);
           // Q tiles of this segment; the buffers were last read by the final S products of segment seg - 1
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -234,18 +277,16 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                           row0 + t * kTileM, hh, bb);
           }
 #pragma unroll 1
-          for (int x = 0; x < 2 * n; ++x, ++kvi) {  // ring order K V K V ...
-            const int slot = kvi % kS;
-            const uint32_t use = kvi / kS;
-            mbar_wait(bar_kv_empty(slot), (use & 1) ^ 1, 20);
-            mbar_arrive_expect_tx(bar_kv_full(slot), C::kTileBytes);
-            const CUtensorMap* map = (x & 1) ? &tmap_v : &tmap_k;
-#pragma unroll
-            for (int db = 0; db < kDBlocks; ++db)
-              tma_load_4d(sKV + slot * C::kTileBytes + db * 16384, map, bar_kv_full(slot), db * 64,
-                          (t0 + (x >> 1)) * kTileN, hh, bb);
+          for (int x = k0_loaded ? 1 : 0; x < 2 * n; ++x) load_kv(x, t0, hh, bb);
+          wk.next(T);
+          // The next segment's first S needs its K tile as much as its Q tiles, and the Q loads wait for the
+          // last S products of this segment: send that K tile first (its ring slot is free long before).
+          k0_loaded = wk.more();
+          if (k0_loaded) {
+            int row0n, hhn, bbn;
+            unit_coords(wk.unit(cta, G), row0n, hhn, bbn);
+            load_kv(0, wk.first(), hhn, bbn);
           }
-          wk.next();
         }
       }
       __syncwarp();
@@ -311,7 +352,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
         int g = 0;  // KV tiles processed so far by this CTA; ring indices are 2g (K) and 2g+1 (V)
         if (wk.more()) {
-          const int n0 = wk.count();
+          const int n0 = wk.count(T);
           wait_kv(0);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -322,10 +363,10 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           release_kv(0);
         }
         for (int seg = 0; wk.more(); ++seg) {
-          const int n = wk.count();
-          wk.next();
+          const int n = wk.count(T);
+          wk.next(T);
           const bool more_segs = wk.more();
-          const int n_next = more_segs ? wk.count() : 0;
+          const int n_next = more_segs ? wk.count(T) : 0;
 #pragma unroll 1
           for (int j = 0; j < n; ++j, ++g) {
             const bool first = (j == 0), last = (j == n - 1);
@@ -366,6 +407,64 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
       }
       __syncwarp();
+    } else if (warp == 18) {
+      // =======================================================================================
+      // store warp: O staging tile -> global (TMA), off the softmax warps' critical path
+      // =======================================================================================
+      if (elect_one()) {
+        int k = 0;  // staging turn
+        for (; wk.more(); wk.next(T)) {
+          const int n = wk.count(T);
+          const int t0 = wk.first();
+          if (t0 > 0) {
+            // producer part: publish each tile's partial once its 8 warps have stored it.  mbarrier arrive /
+            // wait order the warps' global stores before this thread's release store, which is cumulative.
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(bar_part_done(t), 0, 59);
+              asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + cta * 2 + t), "r"(1)
+                           : "memory");
+            }
+            continue;
+          }
+          const int unit = wk.unit(cta, G);
+          int row0, hh, bb;
+          unit_coords(unit, row0, hh, bb);
+          int parts = 0;
+          if (n < T) {
+            // consumer part (the last thing this CTA does): watch the flags of the rest of the unit while the
+            // KV loop runs, so that the softmax warps find them raised
+            const long long unit_end = static_cast<long long>(unit - p.sk_dp * G + 1) * T;
+            for (int c2 = cta + 1; c2 < G && p.sk_W * c2 / G < unit_end; ++c2) ++parts;
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+              for (int i = 1; i <= parts; ++i) {
+                const int* flag = p.sk_flags + (cta + i) * 2 + t;
+                int v;
+                do {
+                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                } while (v == 0);
+              }
+              mbar_arrive(bar_parts_ready(t));
+            }
+          }
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t, ++k) {
+            mbar_wait(bar_stage_full, k & 1, 58);
+#pragma unroll
+            for (int db = 0; db < kDBlocks; ++db)
+              tma_store_4d(&tmap_o, sStage + db * 16384, db * 64, row0 + t * kTileM, hh, bb);
+            tma_store_commit();
+            // every thread of the tile has read the partials before it arrived: lower the flags
+            for (int i = 1; i <= parts; ++i)
+              asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (cta + i) * 2 + t), "r"(0)
+                           : "memory");
+            tma_store_wait_read();  // the staging tile may be rewritten once the store has read it
+            mbar_arrive(bar_stage_free);
+          }
+        }
+      }
+      __syncwarp();
     }
   } else {
     // =========================================================================================
@@ -379,23 +478,16 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint32_t tS = tmem + lane_base + col_s(t) + half * 64;
     const uint32_t tO = tmem + lane_base + col_o(t) + half * kOHalf;
     const int pair_bar = 1 + t * 4 + (warp & 3);
-    const int tile_bar = 9 + t;  // the 8 warps of my tile
     float* my_max = sMax + (t * 2 + half) * 128 + r;
     const float* other_max = sMax + (t * 2 + (half ^ 1)) * 128 + r;
-    const bool tile_leader = ((warp & 7) == 0) && lane == 0;
-    // my float4 column q of a partial lives at part_o[q * 128] (see SkSlot)
-    const size_t part_o_off = (static_cast<size_t>((t * 2 + half) * kQ4) * 128 + r) * 4;
-    const size_t part_ml_off = SkSlot<kDP>::kOFloats + (t * kTileM + r) * 2;
+    [[maybe_unused]] const bool tile_leader = ((warp & 7) == 0) && lane == 0;  // FA_TRACE stamps
 
     int g = 0;
+    int stage_use = 0;  // staging turns taken so far by final (non-producer) segments, two per segment
+    FA_SK_TR(0);
     for (int seg = 0; wk.more(); ++seg) {
-      const int n = wk.count();
+      const int n = wk.count(T);
       const int t0 = wk.first();
-      const int kind = (t0 > 0) ? 1 : (n < T ? 2 : 0);
-      const int unit = wk.unit();
-      int row0, hh, bb;
-      unit_coords(unit, row0, hh, bb);
-      const int tile_row0 = row0 + t * kTileM;
       float m_run = -INFINITY;
       float l_run = 0.f;
 
@@ -412,17 +504,36 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                     bar_p_late(t), 0u, bar_p_mid(t));
       }
 
-      // ---- end of the pass over this unit's KV range
-      sFinal[(t * 2 + half) * 128 + r] = l_run;
+      // ---- end of the pass over this unit's KV range.  Everything the epilogue needs is derived here, behind
+      // an opaque zero, so that none of it occupies registers during the KV loop.
+      FA_SK_TR(1 + 3 * seg);
+      const int z = opaque_zero();
+      const int rz = r + z;
+      sFinal[(t * 2 + half) * 128 + rz] = l_run;
       named_bar_sync(pair_bar, 64);
-      float l_tot = l_run + sFinal[(t * 2 + (half ^ 1)) * 128 + r];
-      const int row = tile_row0 + r;
-      const int use = 2 * seg + t;  // my turn on the O staging tile
-      mbar_wait(bar_o_final(t), seg & 1, 54 + t);
-      tc_fence_after();
+      float l_tot = l_run + sFinal[(t * 2 + (half ^ 1)) * 128 + rz];
+      const int kind = (t0 > 0) ? 1 : (n < T ? 2 : 0);
+      const int unit = wk.unit(cta, G) + z;
+      int row0, hh, bb;
+      unit_coords(unit, row0, hh, bb);
+      const int tile_row0 = row0 + t * kTileM;
+      const int row = tile_row0 + rz;
+      // my float4 column q of a partial lives at part_o[q * 128] (see SkSlot)
+      const size_t part_o_off = (static_cast<size_t>((t * 2 + half) * kQ4) * 128 + rz) * 4;
+      const size_t part_ml_off = SkSlot<kDP>::kOFloats + (t * kTileM + rz) * 2;
+      int parts = 0;  // consumer part: the rest of my unit is held by CTAs cta+1 .. cta+parts
+      if (kind == 2) {
+        const long long unit_end = static_cast<long long>(unit - p.sk_dp * G + 1) * T;
+        for (int c2 = cta + 1; c2 < G && p.sk_W * c2 / G < unit_end; ++c2) ++parts;
+      }
+      // my turn on the O staging tile (producer parts take none)
+      const int use = stage_use + t;
+      if (kind != 1) stage_use += 2;
 
       if (kind == 1) {
         // producer: unnormalised O row-half, and (m, l) by the half-0 thread, to my workspace slot
+        mbar_wait(bar_o_final(t), seg & 1, 54 + t);
+        tc_fence_after();
         float* slot = p.sk_ws + static_cast<size_t>(cta) * SkSlot<kDP>::kFloats;
         float4* o_dst = reinterpret_cast<float4*>(slot + part_o_off);
 #pragma unroll
@@ -441,33 +552,17 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tile_free(t));
         if (half == 0) __stcg(reinterpret_cast<float2*>(slot + part_ml_off), make_float2(m_run, l_tot));
-        __threadfence();
-        named_bar_sync(tile_bar, 256);
-        if (tile_leader) {
-          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + cta * 2 + t), "r"(1)
-                       : "memory");
-          // pass my turn on the staging tile on (a producer part does not use it)
-          if (use > 0) mbar_wait(bar_stage, (use - 1) & 1, 56);
-          mbar_arrive(bar_stage);
-        }
+        // the store warp raises the flag (release at gpu scope) once all 8 warps of the tile are here;
+        // nobody on the softmax side waits for that
         __syncwarp();
+        if (lane == 0) mbar_arrive(bar_part_done(t));
       } else {
         float f_mine = 1.f;
-        int parts = 0;  // producer parts of my unit: CTAs cta+1 .. cta+parts
         if (kind == 2) {
-          const long long unit_end = static_cast<long long>(unit - p.sk_dp * G + 1) * T;
-          for (int c2 = cta + 1; c2 < G && p.sk_W * c2 / G < unit_end; ++c2) ++parts;
-          // wait for the partials of the rest of the unit, then find the common maximum and the row sum
-          if (tile_leader) {
-            for (int i = 1; i <= parts; ++i) {
-              const int* flag = p.sk_flags + (cta + i) * 2 + t;
-              int v;
-              do {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-              } while (v == 0);
-            }
-          }
-          named_bar_sync(tile_bar, 256);
+          // the partials of the rest of the unit (the store warp watched the flags during the KV loop):
+          // common maximum and row sum
+          mbar_wait(bar_parts_ready(t), 0, 55);
+          FA_SK_TR(2 + 3 * seg);
           float m_all = m_run;
           for (int i = 1; i <= parts; ++i) {
             const float* slot = p.sk_ws + static_cast<size_t>(cta + i) * SkSlot<kDP>::kFloats;
@@ -486,8 +581,10 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           p.lse[static_cast<int64_t>(unit / p.sk_P) * p.Nq + row] = m_run * c + log2f(l_tot);
         const float inv_l = 1.f / l_tot;
         f_mine *= inv_l;
+        mbar_wait(bar_o_final(t), seg & 1, 54 + t);
+        tc_fence_after();
         // my turn on the staging tile: the previous user's TMA store has read it
-        if (use > 0) mbar_wait(bar_stage, (use - 1) & 1, 57);
+        if (use > 0) mbar_wait(bar_stage_free, (use - 1) & 1, 57);
         uint8_t* stage = smem + C::kStage;
 #pragma unroll
         for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
@@ -525,26 +622,15 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             val.y = pack2<kBF16>(of[ch * 8 + 2], of[ch * 8 + 3]);
             val.z = pack2<kBF16>(of[ch * 8 + 4], of[ch * 8 + 5]);
             val.w = pack2<kBF16>(of[ch * 8 + 6], of[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kOHalf + cidx * 32 + ch * 8)) = val;
+            *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(rz, half * kOHalf + cidx * 32 + ch * 8)) = val;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(tile_bar, 256);
-        if (tile_leader) {
-#pragma unroll
-          for (int db = 0; db < kDBlocks; ++db)
-            tma_store_4d(&tmap_o, sStage + db * 16384, db * 64, tile_row0, hh, bb);
-          tma_store_commit();
-          tma_store_wait_read();  // the staging tile may be rewritten once the store has read it
-          mbar_arrive(bar_stage);
-          // every thread of the tile has read the partials (barrier above): lower the flags
-          for (int i = 1; i <= parts; ++i)
-            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (cta + i) * 2 + t), "r"(0)
-                         : "memory");
-        }
         __syncwarp();
+        if (lane == 0) mbar_arrive(bar_stage_full);  // the store warp takes it from here
       }
-      wk.next();
+      FA_SK_TR(3 + 3 * seg);
+      wk.next(T);
     }
   }
 

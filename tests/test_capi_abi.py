@@ -56,10 +56,12 @@ def _st(B, H, N, D):
 @pytest.mark.parametrize(
     "shape,expected",
     [
-        ((1, 16, 8192, 8192, 128), _capi.FA_KERNEL_SK),       # BASELINE sweep point: 512 blocks >= 2 x 148 SMs
-        ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # 256 blocks < 2 per SM: one-shot kernel
-        ((1, 16, 16384, 16384, 128), _capi.FA_KERNEL_WS2),    # 1024 blocks = 6.92 rounds, long KV loop: two-tile kernel on CTA pairs
-        ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),      # BASELINE config 5: 110.7 rounds, one-shot
+        ((1, 16, 8192, 8192, 128), _capi.FA_KERNEL_SK),       # BASELINE sweep point: 3.46 rounds of work, 4 one-shot rounds
+        ((1, 16, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # 1.73 rounds: the split's L2 round trip eats the gain (model: tie)
+        ((1, 16, 16384, 16384, 128), _capi.FA_KERNEL_WS),     # 6.92 rounds: 1 % to gain, one-shot kernel (ws2 retired from auto)
+        ((64, 16, 4096, 4096, 128), _capi.FA_KERNEL_SK),      # BASELINE config 5: 110.7 rounds, cheap unit boundaries add up
+        ((8, 16, 4096, 4096, 128), _capi.FA_KERNEL_SK),       # config 5 shard on 8 GPUs: 13.84 rounds
+        ((1, 37, 4096, 4096, 128), _capi.FA_KERNEL_WS),       # 592 units = 4 x 148: nothing to balance
         ((1, 2, 128, 128, 64), _capi.FA_KERNEL_TC1),          # BASELINE config 1 shape
         ((3, 7, 1537, 1234, 112), _capi.FA_KERNEL_WS),        # precision_test.py after D pad
         ((1, 16, 1024, 1024, 128), _capi.FA_KERNEL_WIDE),     # sweep point: 128 tiles <= 148 SMs, one round of one-tile CTAs
