@@ -196,11 +196,12 @@ int choose_kernel_shape(const Problem& p) {
   if (p.D <= 64 && tiles128 > 148 && p.Nkv >= 4 * fa::kTileN && (!p.causal || blocks256 >= 2 * 148))
     return FA_KERNEL_WS3;
   if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
-  // Causal with fewer than two 256-row blocks per SM: the one-tile arrangement halves the scheduling
-  // grain, which matters more than its extra K/V traffic while the triangle leaves SMs idle (measured
-  // fp16 H=16 N=4096 causal: 763 vs 726 TFLOPS at D=128, 412 vs 360 at D=64; at N=16384 ws wins).
-  if (p.causal && static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM)) < 2 * 148)
-    return FA_KERNEL_WIDE;
+  // Causal problems whose 256-row blocks all fit in one round: the launch lasts as long as its longest block, so
+  // the one-tile arrangement's 128-row grain wins although it moves twice the K/V per Q tile.  Beyond one round
+  // the two-tile kernel is ahead again - since round 2 causal launches run longest block first across heads
+  // (fa::work_coords), which took N=4096 from 90 to 62 us.  fp16 H=16, wide / ws in us (profiles/r02_sweep_kernels
+  // .json): D=128 N=2048 23.7 / 32.0, N=4096 72.3 / 62.0, N=8192 256 / 225; D=64 N=2048 20.7 / 30.8, N=4096 64.8 / 58.6.
+  if (p.causal && blocks256 <= 148) return FA_KERNEL_WIDE;
   // Any mask, when every 128-row tile gets its own SM in one round: twice the CTAs of the two-tile kernel
   // and a shorter iteration (graph-timed, fp16 H=16 D=128: N=512 252 vs 179 TFLOPS, N=1024 654 vs 460;
   // at N=2048 - 256 tiles, two rounds - the two-tile kernel is back in front, 1081 vs 875).
@@ -313,6 +314,13 @@ int launch_fwd(void (*kernel)(KArgs...), dim3 grid, int threads, int smem, cudaS
   return FA_OK;
 }
 
+// Launch grid over (row blocks per head, H, B): 3-D as is for non-causal problems, flattened to one dimension
+// for causal ones, where the kernels order the blocks longest first across heads (fa::work_coords).
+dim3 block_grid(long long blocks_per_head, const Problem& p) {
+  if (p.causal) return dim3(static_cast<unsigned>(blocks_per_head * p.H * p.B), 1, 1);
+  return dim3(static_cast<unsigned>(blocks_per_head), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
+}
+
 template <int kDP, bool kBF16, bool kCausal>
 int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   const Problem& p = pl.p;
@@ -322,7 +330,7 @@ int launch_ws(const Plan& pl, float* lse, cudaStream_t stream) {
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
-  dim3 grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p.H, p.B);
+  const dim3 grid = block_grid((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM), p);
   return launch_fwd(kernel, grid, fa::kWsThreads, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
@@ -478,7 +486,7 @@ int launch_tc1(const Plan& pl, float* lse, cudaStream_t stream) {
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
-  dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
+  const dim3 grid = block_grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p);
   return launch_fwd(kernel, grid, 128, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
@@ -491,7 +499,7 @@ int launch_wide(const Plan& pl, float* lse, cudaStream_t stream) {
   int rc = set_smem(kernel, smem, &configured, pl.device);
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
-  dim3 grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p.H, p.B);
+  const dim3 grid = block_grid((p.Nq + fa::kTileM - 1) / fa::kTileM, p);
   return launch_fwd(kernel, grid, fa::kWideThreads, smem, stream, pl.mq, pl.mk, pl.mv, pl.mo, tp);
 }
 
@@ -521,7 +529,7 @@ int launch_ws3(const Plan& pl, float* lse, cudaStream_t stream) {
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   const int blocks = (p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM);
-  dim3 grid((blocks + 1) & ~1, p.H, p.B);
+  const dim3 grid = block_grid((blocks + 1) & ~1, p);
   return launch_fwd(kernel, grid, fa::kWsThreads, smem, stream, pl.mq, pl.mk64, pl.mv, pl.mo, tp);
 }
 
@@ -536,7 +544,7 @@ int launch_wide2(const Plan& pl, float* lse, cudaStream_t stream) {
   if (rc) return rc;
   fa::TcParams tp{lse, p.Nq, p.Nkv, p.H, p.scale * 1.4426950408889634f, nullptr, nullptr, 0, 0, 0, 0 FA_TP_TRACE};
   const int tiles = (p.Nq + fa::kTileM - 1) / fa::kTileM;
-  dim3 grid((tiles + 1) & ~1, p.H, p.B);  // whole pairs: an odd last tile gets a partner that is all padding
+  const dim3 grid = block_grid((tiles + 1) & ~1, p);  // whole pairs: an odd last tile gets a partner that is all padding
   return launch_fwd(kernel, grid, fa::kWideThreads, smem, stream, pl.mq, pl.mk64, pl.mv, pl.mo, tp);
 }
 

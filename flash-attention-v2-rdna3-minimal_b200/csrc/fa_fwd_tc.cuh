@@ -31,6 +31,31 @@ struct TcParams {
 #endif
 };
 
+// Work item of a CTA (or CTA pair): index `blk` of its row block inside a (batch, head), and (h, b).
+//   non-causal  3-D grid (blocks per head, H, B), as launched
+//   causal      1-D grid ordered longest block first ACROSS heads: linear index L -> block rank L / (B H),
+//               head L % (B H).  A CTA's work grows with its block index (it visits the KV tiles up to its
+//               diagonal), and the hardware dispatches CTAs in index order: with the 3-D grid every head's long
+//               blocks queue up behind the short blocks of the heads before it and the launch ends on a few long
+//               stragglers (fp16 H=16 D=128 N=4096: 90 us for 50 us of work per SM); longest-first over the whole
+//               launch is the classic LPT list schedule.  `unit` = 1 for one CTA per block, 2 for CTA pairs
+//               (gridDim.x counts CTAs).
+template <bool kCausal>
+__device__ __forceinline__ void work_coords(int blocks_per_head, int H, int unit, int& blk, int& h, int& b) {
+  if constexpr (kCausal) {
+    const int L = static_cast<int>(blockIdx.x) / unit;
+    const int n_bh = (static_cast<int>(gridDim.x) / unit) / blocks_per_head;
+    const int bh = L % n_bh;
+    blk = blocks_per_head - 1 - L / n_bh;
+    h = bh % H;
+    b = bh / H;
+  } else {
+    blk = static_cast<int>(blockIdx.x) / unit;
+    h = blockIdx.y;
+    b = blockIdx.z;
+  }
+}
+
 constexpr int kTileM = 128;  // query rows per tile
 constexpr int kTileN = 128;  // keys per tile
 
@@ -69,9 +94,8 @@ fa_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int qtile = kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // longest tiles first
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  int qtile, h, b;  // causal: longest tiles first across the whole launch (work_coords)
+  work_coords<kCausal>((p.Nq + kTileM - 1) / kTileM, p.H, 1, qtile, h, b);
   const int row0 = qtile * kTileM;
 
   if (tid == 0) {

@@ -80,9 +80,8 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int qtile = kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // longest tiles first
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  int qtile, h, b;  // causal: longest tiles first across the whole launch (work_coords)
+  work_coords<kCausal>((p.Nq + kTileM - 1) / kTileM, p.H, 1, qtile, h, b);
   const int row0 = qtile * kTileM;
 
   int n = (p.Nkv + kTileN - 1) / kTileN;  // KV tiles this Q tile visits (>= 1)

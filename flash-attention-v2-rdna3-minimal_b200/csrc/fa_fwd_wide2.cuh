@@ -87,11 +87,9 @@ fa_fwd_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   // the pair is Q tiles (2p, 2p+1); the grid is padded to an even number of tiles; causal: longest pairs first
-  const int pair = kCausal ? (static_cast<int>(gridDim.x / 2) - 1 - static_cast<int>(blockIdx.x / 2))
-                           : static_cast<int>(blockIdx.x / 2);
+  int pair, h, b;
+  work_coords<kCausal>(((p.Nq + kTileM - 1) / kTileM + 1) / 2, p.H, 2, pair, h, b);
   const int qtile = 2 * pair + static_cast<int>(rank);
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int row0 = qtile * kTileM;
   // KV tiles: the two CTAs advance in lock step, so under a causal mask both visit the tiles the LATER Q
   // tile needs (2p + 2 of them); the extra tile is fully masked for the earlier one (P = 0, nothing added)

@@ -292,13 +292,11 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int pair = kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // longest blocks first
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  int pair, h, b;  // causal: longest blocks first across the whole launch (work_coords)
+  work_coords<kCausal>((p.Nq + 2 * kTileM - 1) / (2 * kTileM), p.H, 1, pair, h, b);
   const int row0 = pair * 2 * kTileM;
 #ifdef FA_TRACE
-  const bool tr_cta = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 &&
-                      blockIdx.z == 0;
+  const bool tr_cta = p.trace != nullptr && pair == (p.Nq + 2 * kTileM - 1) / (2 * kTileM) / 2 && h == 0 && b == 0;
   const bool tr_on = tr_cta && (warp >= 16 || (warp & 7) == 0 || warp == 4);  // warp 4: partner of warp 0
 #endif
 

@@ -262,11 +262,9 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   // 256-row query block; the pair is blocks (2p, 2p+1), grid padded to even; causal: longest pairs first
-  const int pair = kCausal ? (static_cast<int>(gridDim.x / 2) - 1 - static_cast<int>(blockIdx.x / 2))
-                           : static_cast<int>(blockIdx.x / 2);
+  int pair, h, b;
+  work_coords<kCausal>(((p.Nq + 2 * kTileM - 1) / (2 * kTileM) + 1) / 2, p.H, 2, pair, h, b);
   const int blk = 2 * pair + static_cast<int>(rank);
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
   const int row0 = blk * 2 * kTileM;
   // KV tiles: the four Q tiles of the pair advance in lock step, so under a causal mask all visit the tiles the LAST
   // one needs (4 pair + 4); the extra tiles are fully masked for the earlier ones (P = 0, nothing is added)

@@ -1,4 +1,4 @@
-"""Drop-in for /root/reference/rocwmma_fattn/FlashAttn.py (forward, and backward for head dims <= 128).
+"""Drop-in for /root/reference/rocwmma_fattn/FlashAttn.py (forward and backward).
 
 Same entry point and calling convention as the reference::
 
@@ -34,7 +34,7 @@ __all__ = [
 
 _TMA_D_ALIGN = 8  # head dim multiple of 16 bytes for the tensor-core (TMA) kernels
 _TC_MAX_D = 256      # forward: ws / sk / tc1 kernels up to 128, the wide kernel up to 256
-_TC_MAX_D_BWD = 128  # backward kernels
+_TC_MAX_D_BWD = 128  # tcgen05 backward kernel; larger head dims run the generic CUDA-core backward
 
 
 def _raw_stream(dev_index: int) -> int:
@@ -71,6 +71,14 @@ def _prepare(t: torch.Tensor, d_pad: int) -> torch.Tensor:
     if t.stride(-1) != 1:
         t = t.contiguous()  # kernel_fp16.cu:780-787
     return t
+
+
+def _tma_view(t: torch.Tensor) -> torch.Tensor:
+    """`t` itself if TMA can address it (16-byte aligned base, strides multiples of 8 elements), else a
+    contiguous copy."""
+    if t.data_ptr() % 16 == 0 and all(st % 8 == 0 for st, n in zip(t.stride()[:3], t.shape[:3]) if n > 1):
+        return t
+    return t.contiguous()
 
 
 def _forward(q, k, v, causal, scale, bnhd, want_lse):
@@ -132,17 +140,21 @@ def _forward(q, k, v, causal, scale, bnhd, want_lse):
 def _backward(qp, kp, vp, o_full, d_o, lse, D, causal, scale, bnhd):
     """dQ, dK, dV on the tensors the forward saved (head dim padded to a multiple of 8).  Replaces
     backward_fp16 / backward_bf16 (kernel_fp16.cu:878-1028): the incoming gradient is zero-padded
-    in the head dim like there (:903-917), the three gradients come back sliced to ``D``."""
+    in the head dim like there (:903-917), the three gradients come back sliced to ``D``.  Head dims up to
+    128 run the tcgen05 kernel, larger ones (the reference pads and serves any, :900) the generic CUDA-core
+    backward (csrc/fa_bwd_simt.cuh)."""
     if not qp.is_cuda:
         raise RuntimeError("rocwmma_fattn (B200 build) runs on CUDA tensors only; there is no CPU fallback")
     DP = qp.shape[3]
-    if DP > _TC_MAX_D_BWD or DP % _TMA_D_ALIGN:
-        raise NotImplementedError(
-            f"the sm_100a backward kernel covers head dims up to {_TC_MAX_D_BWD} (got {D}); larger head "
-            "dims run forward-only in this build")
     if d_o.dtype != qp.dtype:
         d_o = d_o.to(qp.dtype)  # host.cpp:49-57 dispatches on dO's dtype; ours follows q's
     d_o = _prepare(d_o, DP - d_o.shape[3])
+    if DP <= _TC_MAX_D_BWD and DP % _TMA_D_ALIGN == 0:
+        # The tcgen05 backward reads its operands through TMA: 16-byte aligned base pointers and strides.  The
+        # forward serves other views (an odd offset into a packed qkv buffer, a row stride that is not a multiple
+        # of 8) with its generic kernel; the backward makes them contiguous instead, as the reference does for
+        # everything (kernel_fp16.cu:903-917), rather than dropping to the generic backward.
+        qp, kp, vp, o_full, d_o = (_tma_view(t) for t in (qp, kp, vp, o_full, d_o))
     B, H, Nq, _ = _logical_shape(qp, bnhd)
     Nkv = _logical_shape(kp, bnhd)[2]
     dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)

@@ -50,7 +50,7 @@ def supported(query, key, value, attn_mask=None, dropout_p=0.0, enable_gqa=False
 def scaled_dot_product_attention(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False,
                                  scale=None, enable_gqa=False, *, fallback=None):
     """Same positional signature as ``torch.nn.functional.scaled_dot_product_attention``.  Differentiable
-    (head dims <= 128) through ``FlashAttentionFunction.backward``."""
+    through ``FlashAttentionFunction.backward`` (tcgen05 kernel up to head dim 128, generic CUDA kernel above)."""
     why = supported(query, key, value, attn_mask, dropout_p, enable_gqa)
     if why is not None:
         if fallback is None:

@@ -25,7 +25,7 @@ def test_c_consumer_compiles_links_and_reports_the_abi():
     from rocwmma_fattn import _capi
 
     assert fields[0] == "abi" and int(fields[1]) == _capi.FA_ABI_VERSION
-    assert int(fields[3]) == _capi.FA_KERNEL_WS2  # the N=16384 sweep point, selected without a GPU
+    assert int(fields[3]) == _capi.FA_KERNEL_WS  # the N=16384 sweep point, selected without a GPU
 
 
 @pytest.mark.gpu

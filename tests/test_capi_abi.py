@@ -88,15 +88,18 @@ def test_kernel_selection_is_pure_host_logic(shape, expected):
 def test_kernel_selection_causal_head_dim_64():
     st = _st(1, 16, 16384, 64)
     assert _capi.select_kernel(1, 16, 16384, 16384, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WS3
-    st = _st(1, 16, 4096, 64)  # 256 blocks < 2 per SM: the one-tile kernel's 128-row grain
-    assert _capi.select_kernel(1, 16, 4096, 4096, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WIDE
+    st = _st(1, 16, 4096, 64)  # 256 blocks: more than one round, fewer than two - the two-tile kernel (LPT order)
+    assert _capi.select_kernel(1, 16, 4096, 4096, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WS
+    st = _st(1, 16, 2048, 64)  # 128 blocks: one round - the one-tile kernel's 128-row grain
+    assert _capi.select_kernel(1, 16, 2048, 2048, 64, st, st, st, st, _capi.FA_DTYPE_F16, True, 0.125) == _capi.FA_KERNEL_WIDE
 
 
 @pytest.mark.parametrize(
     "n,expected",
     [
-        (4096, _capi.FA_KERNEL_WIDE),   # BASELINE config 4 point: 256 blocks < 2 per SM -> 128-row scheduling grain
-        (8192, _capi.FA_KERNEL_WS),     # 512 blocks: the two-tile kernel's shared K/V traffic wins again
+        (2048, _capi.FA_KERNEL_WIDE),   # BASELINE config 4 point: 128 blocks, one round -> 128-row scheduling grain
+        (4096, _capi.FA_KERNEL_WS),     # 256 blocks, longest first across heads: the two-tile kernel (62 vs 72 us)
+        (8192, _capi.FA_KERNEL_WS),
         (16384, _capi.FA_KERNEL_WS),
         (128, _capi.FA_KERNEL_TC1),
     ],

@@ -164,8 +164,40 @@ def test_backward_baseline_shape_sampled_rows():
                  "sweep shape N=2048")
 
 
-def test_backward_rejects_head_dim_above_128():
-    q, k, v = (t.to(DEV).requires_grad_(True) for t in orc.make_inputs(1, 1, 64, 64, 256, F16, seed=1))
-    o = FlashAttentionFunction.apply(q, k, v, None, False)
-    with pytest.raises(NotImplementedError):
-        o.backward(torch.ones_like(o))
+WIDE_BWD_SHAPES = [
+    # B, H, Nq, Nkv, D: head dims above 128 (the reference pads and serves any, kernel_fp16.cu:900) run the
+    # generic CUDA-core backward (csrc/fa_bwd_simt.cuh)
+    (1, 2, 300, 300, 160),   # SD 1.5 head dim
+    (2, 1, 257, 130, 192),
+    (1, 2, 128, 384, 256),
+    (1, 1, 200, 77, 264),    # above 256: generic forward AND backward
+    (1, 2, 193, 150, 135),   # odd head dim, padded to 136
+]
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [F16, BF16])
+@pytest.mark.parametrize("shape", WIDE_BWD_SHAPES)
+def test_backward_head_dims_above_128_match_fp32_autograd(shape, dtype, causal):
+    B, H, Nq, Nkv, D = shape
+    q, k, v = orc.make_inputs(B, H, Nq, Nkv, D, dtype, seed=sum(shape) + int(causal))
+    g = torch.Generator().manual_seed(5 + sum(shape))
+    d_o = torch.rand((B, H, Nq, D), generator=g).to(dtype)
+    ref, b16 = truth(q, k, v, d_o, causal)
+    n0 = _capi.launch_count()
+    _, dq, dk, dv = grads(q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV), causal)
+    assert _capi.launch_count() == n0 + 1 + 3  # forward; pre-pass, dQ kernel, dK/dV kernel
+    assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal} (generic backward)")
+
+
+def test_backward_of_unaligned_views_takes_the_tensor_core_kernel_on_contiguous_copies():
+    """the forward serves views TMA cannot address (an odd element offset into a packed buffer)
+    with its generic kernel; the backward must not fail on the tensors it saved."""
+    B, H, N, D = 1, 2, 256, 64
+    base = torch.rand((3, B, H, N, D + 4), generator=torch.Generator().manual_seed(3)).to(F16).to(DEV)
+    q, k, v = (base[i, ..., 2:2 + D] for i in range(3))  # last stride 1, row stride 68, base offset 4 bytes
+    assert q.data_ptr() % 16 != 0 and q.stride(2) % 8 != 0
+    d_o = torch.rand((B, H, N, D), generator=torch.Generator().manual_seed(4)).to(F16).to(DEV)
+    _, dq, dk, dv = grads(q, k, v, d_o, True)
+    ref, b16 = truth(q, k, v, d_o, True)
+    assert_grads((dq, dk, dv), ref, b16, F16, "unaligned views")
