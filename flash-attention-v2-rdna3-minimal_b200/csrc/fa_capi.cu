@@ -226,7 +226,7 @@ struct Plan {
   Problem p;
   int device;
   CUtensorMap mq, mk, mv, mo;
-  CUtensorMap mk64;  // K with a 64-key box (CTA-pair kernel: each CTA loads half of a K tile)
+  CUtensorMap mk64;  // K with a 64-key box (CTA-pair kernels: each CTA loads half of a K tile)
   uint64_t stamp;
 };
 

@@ -8,6 +8,7 @@ fp16 and 8 in bf16, and so do the probabilities P.  Test: run the SAME kernel (N
   f16_as_bf16   the same values rounded to bf16 precision, stored as fp16 (fp16 kernel, bf16-like bit patterns)
   f16_const     all 0.5 (nothing toggles)
   bf16_rand     U[0,1) bf16
+  lib:*         the same inputs through torch SDPA (cuDNN fused attention), for its clock and cycle efficiency
 and sample nvidia-smi (SM clock, power) during each.  If the clock, not the cycle count, explains the gap, the
 TFLOPS ratio follows the clock ratio and f16_as_bf16 lands between.
 
@@ -67,8 +68,13 @@ def make(kind):
 smi = Smi()
 time.sleep(0.5)
 out = {}
-for kind in ("f16_rand", "f16_as_bf16", "f16_const", "bf16_rand", "f16_rand"):
-    sets = [tuple(make(kind) for _ in range(3)) for _ in range(2)]
+def lib(q, k, v, _m, causal):
+    return torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
+
+
+for kind in ("f16_rand", "f16_as_bf16", "f16_const", "bf16_rand", "f16_rand", "lib:f16_rand", "lib:bf16_rand", "lib:f16_const"):
+    fa = lib if kind.startswith("lib:") else FlashAttentionFunction.apply
+    sets = [tuple(make(kind.split(":")[-1]) for _ in range(3)) for _ in range(2)]
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
