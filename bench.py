@@ -251,18 +251,21 @@ def time_graph(g, reps, launch_ms_hint=None, launches=100, warm=10):
     """Device time (ms) of one launch, by the reference's own protocol (bench_with_sdpa.py:13,21-31: 10 warm-up
     calls, then 100 calls back to back, one clock reading on each side) - with CUDA events instead of the wall
     clock and the calls pre-recorded in a graph of ``reps`` launches on rotating inputs, because a forward at
-    N <= 2048 is shorter than the Python cost of a call.  No host synchronisation between replays.  At N = 16384
-    the 100 launches last ~150 ms, i.e. the figure is taken at the clock the part sustains under its power cap;
-    at N = 512 they last under 1 ms.  Median of 3."""
+    N <= 2048 is shorter than the Python cost of a call.  No host synchronisation between replays.  The part is
+    power-capped, so what a measurement reads depends on what ran just before it; every measurement (ours and the
+    library's alike) therefore starts from the same state: warm-up, 0.2 s idle, then the 100 launches.  At
+    N = 16384 they last ~150 ms, i.e. mostly at the clock the part sustains under its power cap; at N = 512 under
+    1 ms.  Mean of 2 such runs."""
     if launch_ms_hint and launch_ms_hint > 3.0:
         launches = 30  # (launches of several milliseconds: 30 are already a sustained-clock measurement)
     n_warm = max(1, -(-warm // reps))
     n_rep = max(1, -(-launches // reps))
-    for _ in range(n_warm):
-        g.replay()
-    torch.cuda.synchronize()
     ts = []
-    for _ in range(3):
+    for _ in range(2):
+        for _ in range(n_warm):
+            g.replay()
+        torch.cuda.synchronize()
+        time.sleep(0.2)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(n_rep):
@@ -270,7 +273,7 @@ def time_graph(g, reps, launch_ms_hint=None, launches=100, warm=10):
         a1.record()
         torch.cuda.synchronize()
         ts.append(a0.elapsed_time(a1) / (reps * n_rep))
-    return sorted(ts)[1]
+    return sum(ts) / len(ts)
 
 
 def time_variant(fn, pool, causal, flops_per_call):
@@ -604,8 +607,8 @@ def main():
                    "parity": {"checked": "max|o - fp32 attention| over all rows of all heads, on the device, per sweep point",
                               "ok": parity_ok},
                    "per_n_protocol": "the reference's: 10 warm-up + 100 back-to-back launches per sequence length "
-                                     "(bench_with_sdpa.py:13,21-31; 30 for launches above 3 ms), CUDA events, rotating inputs > 2x L2; "
-                                     "median of 3",
+                                     "(bench_with_sdpa.py:13,21-31; 30 for launches above 3 ms) after 0.2 s of idle, CUDA events, "
+                                     "rotating inputs > 2x L2; mean of 2; the library rows are measured the same way",
                    "per_n": per_n},
         "roofline": roofline,
         "gpu_launches": int(launches),

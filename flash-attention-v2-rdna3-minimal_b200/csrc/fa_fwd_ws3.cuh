@@ -489,21 +489,7 @@ fa_fwd_ws3_kernel(const __grid_constant__ CUtensorMap tmap_q,
     mbar_wait(bar_o_final(t), 0, 54 + t);  // every MMA that touches tile t (of both CTAs) is done
     tc_fence_after();
     uint8_t* stage = smem + C::kQ + t * C::kTileBytes;
-#pragma unroll
-    for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
-      uint32_t o[32];
-      tmem_ld_x32(tO + cidx * 32, o);
-      tmem_wait_ld();
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint4 val;
-        val.x = pack2<kBF16>(__uint_as_float(o[ch * 8 + 0]) * inv_l, __uint_as_float(o[ch * 8 + 1]) * inv_l);
-        val.y = pack2<kBF16>(__uint_as_float(o[ch * 8 + 2]) * inv_l, __uint_as_float(o[ch * 8 + 3]) * inv_l);
-        val.z = pack2<kBF16>(__uint_as_float(o[ch * 8 + 4]) * inv_l, __uint_as_float(o[ch * 8 + 5]) * inv_l);
-        val.w = pack2<kBF16>(__uint_as_float(o[ch * 8 + 6]) * inv_l, __uint_as_float(o[ch * 8 + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kOHalf + cidx * 32 + ch * 8)) = val;
-      }
-    }
+    o_row_half_to_stage<kOHalf, kBF16, true>(tO, stage, r, half, inv_l);
     fence_proxy_async_smem();
     named_bar_sync(9 + t, 256);
     if ((warp & 7) == 0 && lane == 0) {
