@@ -324,7 +324,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int row0 = pair * 2 * kTileM;
 #ifdef FA_TRACE
   const bool tr_cta = p.trace != nullptr && pair == (p.Nq + 2 * kTileM - 1) / (2 * kTileM) / 2 && h == 0 && b == 0;
-  const bool tr_on = tr_cta && (warp >= 16 || (warp & 7) == 0 || warp == 4);  // warp 4: partner of warp 0
+  const bool tr_on = tr_cta && (warp >= 16 || (warp & 7) == 0);  // (row 3 of the trace: fine stamps of the MMA thread)
 #endif
 
   // per-tile KV trip counts
@@ -462,7 +462,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
             umma_ss2(tmem + col_s(t), q_lo + off, desc_hi, k_lo + off, desc_hi, idesc_s, k > 0);
           }
+          if (t == 1) FA_TR(3, j - 1, 0);
           tc_commit(bar_s_full(t));
+          if (t == 1) FA_TR(3, j - 1, 1);
         };
         // k-step ks covers keys [16 ks, 16 ks + 16): P columns of half ks/4 at S column
         // 64 (ks/4) + 8 (ks%4); V rows 16 ks of the tile (2048 bytes apart in the MN-major tile)
@@ -524,8 +526,11 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           FA_TR(2, j, 4);
           if (j < n_t[1]) issue_pv(1, j);
           FA_TR(2, j, 6);
+          FA_TR(3, j, 3);
           release_kv(2 * j + 1);
+          FA_TR(3, j, 4);
           if (nx < n_t[1]) issue_s(1, nx);
+          FA_TR(3, j, 2);
           if (nx < n_max) release_kv(2 * nx);
           FA_TR(2, j, 7);
         }
