@@ -1,0 +1,454 @@
+// Warp-specialised, software-pipelined tcgen05 backward kernel ("bwd ws", round 2).
+//
+// Same mathematics and the same CTA decomposition as fa_bwd_tc.cuh (one CTA per 128-key K/V tile walking the query
+// tiles; reference: /root/reference/rocwmma_fattn/kernel_fp16.cu:547-740, launchers :878-1028), arranged so that the
+// tensor cores, the TMA loads, the P / dS pass and the dQ drain all overlap:
+//
+//   * scores are computed TRANSPOSED, S^T = K_j Q_i^T and dP^T = V_j dO_i^T (TMEM lane = key), so P^T and dS^T -
+//     rounded to 16 bit and written back over their own accumulators - feed dV += P^T dO_i and dK += dS^T Q_i
+//     straight from tensor memory (tcgen05.mma TS form): no P tile in shared memory and half the operand traffic for
+//     two of the five products (shared-memory bandwidth, 128 B/clk, is what bounds the serial kernel);
+//   * dS^T also goes to shared memory ONCE, row-major as each thread holds it ([key][query], eight 16-byte stores per
+//     thread), and feeds dQ_i = dS K_j as an MN-major A operand;
+//   * dQ_i lands over the dP^T columns and is taken out by FOUR DEDICATED WARPS (TMEM -> registers, which frees the
+//     columns at once; then registers -> per-warp fp32 staging -> TMA reduce-add into the fp32 accumulator), so the
+//     P / dS warps never touch dQ and the next dP^T waits only for the register read-out;
+//   * one thread issues every MMA in the order  dV(i) S^T(i+1) dK(i) dQ(i) dP^T(i+1):  P^T(i+1) is computed while
+//     dK(i) / dQ(i) run, dS(i+1) while dV(i+1) / S^T(i+2) run;
+//   * a producer warp keeps Q two tiles ahead (two buffers), dO one tile ahead (one buffer, re-loaded under
+//     S^T / dK / dQ) and stages L_i / D_i of the query tile in shared memory (the transposed threads need them as
+//     vectors over queries, read as broadcasts).
+//
+// 16 warps: 0-7 P / dS (thread = key row r x 64-query half), 8-11 dQ drain (thread = query row), 12 MMA issuer,
+// 13 producer, 14-15 idle (they complete the warpgroup setmaxnreg needs and donate registers).
+// TMEM: S^T [0,128) (P^T of query half h over [64h,64h+32)), dP^T [128,256) (dS^T likewise; dQ_i over [128,128+D)),
+// dV [256,256+D), dK [384,384+D).
+// Shared memory (D = 128): K 32 + V 32 + Q 2x32 + dO 32 + dS 32 + dQ staging 4x2x4 + L/D 2 KB = 226.3 KB.
+#pragma once
+#include "fa_bwd_tc.cuh"
+
+namespace fa {
+
+constexpr int kBwdWsThreads = 512;
+
+template <int kDP>
+struct BwdWsSmem {
+  static constexpr int kTileBytes = kTileM * kDP * 2;
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + kTileBytes;
+  static constexpr int kQ = kV + kTileBytes;                // 2 buffers (dV / dK staging in the epilogue)
+  static constexpr int kdO = kQ + 2 * kTileBytes;           // 1 buffer
+  static constexpr int kdS = kdO + kTileBytes;              // [128 keys][128 q] 16 bit
+  static constexpr int kStage = kdS + kTileM * kTileN * 2;  // 4 warps x 2 x [32 rows][32 fp32]
+  static constexpr int kLD = kStage + 4 * 2 * 4096;         // float [2 buffers][2 (L, D)][128]
+  static constexpr int kBars = kLD + 2 * 2 * 128 * 4;
+  static constexpr int kTotal = kBars + 256;                // no alignment slack: the base is declared 1024-aligned
+};
+
+template <int kDP, bool kBF16, bool kCausal>
+__global__ void __launch_bounds__(kBwdWsThreads, 1)
+fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                 const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v,
+                 const __grid_constant__ CUtensorMap tmap_do,
+                 const __grid_constant__ CUtensorMap tmap_dk,
+                 const __grid_constant__ CUtensorMap tmap_dv,
+                 const __grid_constant__ CUtensorMap tmap_dq32, const BwdParams p) {
+  using L = BwdWsSmem<kDP>;
+  constexpr int kDBlocks = kDP / 64;
+  constexpr int kKSteps = kDP / 16;  // contraction over the head dim (S^T, dP^T)
+  constexpr int kHalfD = kDP / 2;
+  constexpr uint32_t kColS = 0, kColdP = 128, kColdV = 256, kColdK = 384, kColdQ = 128;
+
+  extern __shared__ __align__(1024) uint8_t smem_bwd_ws[];
+  uint8_t* smem = smem_bwd_ws;
+  const uint32_t sK = smem_u32(smem + L::kK);
+  const uint32_t sV = smem_u32(smem + L::kV);
+  const uint32_t sQ = smem_u32(smem + L::kQ);
+  const uint32_t sdO = smem_u32(smem + L::kdO);
+  const uint32_t sdS = smem_u32(smem + L::kdS);
+  float* sLD = reinterpret_cast<float*>(smem + L::kLD);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBars + 128);
+  const uint32_t bar_kv = smem_u32(&bars[0]);                                  // tx
+  auto bar_q_full = [&](int b_) { return smem_u32(&bars[1 + b_]); };           // tx
+  auto bar_ld_full = [&](int b_) { return smem_u32(&bars[3 + b_]); };          // 32 producer lanes
+  auto bar_q_free = [&](int b_) { return smem_u32(&bars[5 + b_]); };           // commit behind dK(i)
+  const uint32_t bar_do_full = smem_u32(&bars[7]);                             // tx
+  const uint32_t bar_do_free = smem_u32(&bars[8]);                             // commit behind dV(i)
+  const uint32_t bar_s = smem_u32(&bars[9]);                                   // commit: S^T ready
+  const uint32_t bar_dp = smem_u32(&bars[10]);                                 // commit: dP^T ready
+  const uint32_t bar_p_ready = smem_u32(&bars[11]);                            // 8 warps: P^T in TMEM
+  const uint32_t bar_ds_ready = smem_u32(&bars[12]);                           // 8 warps: dS^T in TMEM, dS in smem
+  const uint32_t bar_dq = smem_u32(&bars[13]);                                 // commit: dQ_i ready (all earlier MMAs done)
+  const uint32_t bar_drained = smem_u32(&bars[14]);                            // 4 warps: dQ_i is in registers
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int j = blockIdx.x;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int key0 = j * kTileN;
+  const int i_end = (p.Nq + kTileM - 1) / kTileM;
+  const int i_begin = kCausal ? min(j, i_end) : 0;  // query tiles above the diagonal see no key of j
+  const int n_iter = i_end - i_begin;
+  const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+
+  if (tid == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128-byte-swizzled tiles need a 1024-byte-aligned base
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dk);
+    tma_prefetch_desc(&tmap_dv);
+    tma_prefetch_desc(&tmap_dq32);
+    mbar_init(bar_kv, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_q_full(i), 1);
+      mbar_init(bar_ld_full(i), 32);
+      mbar_init(bar_q_free(i), 1);
+    }
+    mbar_init(bar_do_full, 1);
+    mbar_init(bar_do_free, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_p_ready, 8);
+    mbar_init(bar_ds_ready, 8);
+    mbar_init(bar_dq, 1);
+    mbar_init(bar_drained, 4);
+    fence_mbar_init();
+  }
+  if (warp == 12) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_slot != 0u) __trap();  // one CTA per SM owns all 512 columns: literal addresses (see fa_fwd_ws.cuh)
+  constexpr uint32_t tmem = 0u;
+
+  constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kTileN, kBF16, false, false);  // S^T, dP^T
+  constexpr uint32_t idesc_t = make_idesc_f16(kTileM, kDP, kBF16, false, true);      // dV, dK (A from TMEM)
+  constexpr uint32_t idesc_q = make_idesc_f16(kTileM, kDP, kBF16, true, true);       // dQ (A = dS MN-major)
+
+  if (warp >= 12) {
+    setmaxnreg_dec<56>();
+    if (warp == 12) {
+      // =======================================================================================
+      // MMA issuer (one elected thread)
+      // =======================================================================================
+      if (elect_one() && n_iter > 0) {
+        constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+        const uint32_t k_lo = smem_desc_lo(sK, 16), v_lo = smem_desc_lo(sV, 16), do_lo = smem_desc_lo(sdO, 16);
+        const uint32_t do_mn = smem_desc_lo(sdO, 16384), k_mn = smem_desc_lo(sK, 16384), ds_mn = smem_desc_lo(sdS, 16384);
+        auto issue_s = [&](int it) {  // S^T = K Q_i^T
+          const uint32_t q_lo = smem_desc_lo(sQ + (it & 1) * L::kTileBytes, 16);
+#pragma unroll
+          for (int k = 0; k < kKSteps; ++k) {
+            const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+            umma_ss2(tmem + kColS, k_lo + off, desc_hi, q_lo + off, desc_hi, idesc_s, k > 0);
+          }
+          tc_commit(bar_s);
+        };
+        auto issue_dp = [&]() {  // dP^T = V dO_i^T
+#pragma unroll
+          for (int k = 0; k < kKSteps; ++k) {
+            const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+            umma_ss2(tmem + kColdP, v_lo + off, desc_hi, do_lo + off, desc_hi, idesc_s, k > 0);
+          }
+          tc_commit(bar_dp);
+        };
+        mbar_wait(bar_kv, 0, 60);
+        mbar_wait(bar_q_full(0), 0, 61);
+        mbar_wait(bar_do_full, 0, 62);
+        tc_fence_after();
+        issue_s(0);
+        issue_dp();
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+          const int buf = it & 1;
+          const uint32_t q_mn = smem_desc_lo(sQ + buf * L::kTileBytes, 16384);
+          // k-step ks covers queries [16 ks, 16 ks + 16): 16-bit A columns of half ks/4 at 64 (ks/4) + 8 (ks%4) of the
+          // S^T / dP^T accumulator; B rows 16 ks of the dO / Q tile
+          mbar_wait(bar_p_ready, it & 1, 63);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < kTileM / 16; ++ks) {  // dV += P^T dO_i
+            umma_ts2(tmem + kColdV, tmem + kColS + (ks >> 2) * 64 + (ks & 3) * 8, do_mn + ((ks * 2048) >> 4), desc_hi,
+                     idesc_t, (it > 0) || (ks > 0));
+          }
+          tc_commit(bar_do_free);
+          if (it + 1 < n_iter) {  // in order behind dV(i), which read P^T from these columns
+            mbar_wait(bar_q_full(buf ^ 1), ((it + 1) >> 1) & 1, 64);
+            tc_fence_after();
+            issue_s(it + 1);
+          }
+          mbar_wait(bar_ds_ready, it & 1, 65);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < kTileM / 16; ++ks) {  // dK += dS^T Q_i
+            umma_ts2(tmem + kColdK, tmem + kColdP + (ks >> 2) * 64 + (ks & 3) * 8, q_mn + ((ks * 2048) >> 4), desc_hi,
+                     idesc_t, (it > 0) || (ks > 0));
+          }
+          tc_commit(bar_q_free(buf));
+#pragma unroll
+          for (int k = 0; k < kTileN / 16; ++k) {  // dQ_i = dS K_j (contraction over the keys) over the dP^T columns
+            umma_ss2(tmem + kColdQ, ds_mn + ((k * 2048) >> 4), desc_hi, k_mn + ((k * 2048) >> 4), desc_hi, idesc_q,
+                     k > 0);
+          }
+          tc_commit(bar_dq);
+          if (it + 1 < n_iter) {
+            mbar_wait(bar_do_full, (it + 1) & 1, 66);
+            mbar_wait(bar_drained, it & 1, 67);  // dQ(i) has left the dP^T columns
+            tc_fence_after();
+            issue_dp();
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 13) {
+      // =======================================================================================
+      // producer: TMA loads (lane 0) and the L / D vectors of each query tile (all lanes)
+      // =======================================================================================
+      if (n_iter > 0) {
+        auto load_q = [&](int it) {
+          const int buf = it & 1;
+          mbar_arrive_expect_tx(bar_q_full(buf), L::kTileBytes);
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db)
+            tma_load_4d(sQ + buf * L::kTileBytes + db * 16384, &tmap_q, bar_q_full(buf), db * 64,
+                        (i_begin + it) * kTileM, h, b);
+        };
+        auto load_do = [&](int it) {
+          mbar_arrive_expect_tx(bar_do_full, L::kTileBytes);
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db)
+            tma_load_4d(sdO + db * 16384, &tmap_do, bar_do_full, db * 64, (i_begin + it) * kTileM, h, b);
+        };
+        auto stage_ld = [&](int it) {  // rows >= Nq get L = D = 0 (their P is masked)
+          float* dst = sLD + (it & 1) * 256;
+          const int row0 = (i_begin + it) * kTileM + lane * 4;
+          float lv[4], dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool ok = row0 + e < p.Nq;
+            lv[e] = ok ? p.lse[bh * p.Nq + row0 + e] : 0.f;
+            dv[e] = ok ? p.delta[bh * p.Nq + row0 + e] : 0.f;
+          }
+          *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+          *reinterpret_cast<float4*>(dst + 128 + lane * 4) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+          mbar_arrive(bar_ld_full(it & 1));
+        };
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar_kv, 2 * L::kTileBytes);
+#pragma unroll
+          for (int db = 0; db < kDBlocks; ++db) {
+            tma_load_4d(sK + db * 16384, &tmap_k, bar_kv, db * 64, key0, h, b);
+            tma_load_4d(sV + db * 16384, &tmap_v, bar_kv, db * 64, key0, h, b);
+          }
+          load_q(0);
+          load_do(0);
+          if (n_iter > 1) load_q(1);
+        }
+        stage_ld(0);
+        if (n_iter > 1) stage_ld(1);
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) {
+          if (it + 1 < n_iter && lane == 0) {
+            mbar_wait(bar_do_free, it & 1, 68);  // dV(i) done with the dO buffer
+            load_do(it + 1);
+          }
+          if (it + 2 < n_iter) {
+            if (lane == 0) {
+              mbar_wait(bar_q_free(it & 1), (it >> 1) & 1, 69);  // dK(i) done: Q buffer and its L / D vectors are free
+              load_q(it + 2);
+            }
+            __syncwarp();
+            stage_ld(it + 2);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // =========================================================================================
+    // dQ drain warps: thread = query row (TMEM lane) of the tile
+    // =========================================================================================
+    setmaxnreg_inc<168>();
+    const int dw = warp - 8;
+    const uint32_t lane_base = static_cast<uint32_t>(dw * 32) << 16;
+    uint8_t* stage0 = smem + L::kStage + dw * 8192;
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = i_begin + it;
+      mbar_wait(bar_dq, it & 1, 70);
+      tc_fence_after();
+      uint32_t v[kDP];
+#pragma unroll
+      for (int cidx = 0; cidx < kDP / 32; ++cidx) tmem_ld_x32(tmem + lane_base + kColdQ + cidx * 32, v + cidx * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_drained);
+      // registers -> this warp's swizzled fp32 staging tile [32 rows][32 columns] -> TMA reduce-add into
+      // dq_acc[b,h, 32 rows, 32 columns] (rows >= Nq are clipped by the tensor map)
+#pragma unroll
+      for (int cidx = 0; cidx < kDP / 32; ++cidx) {
+        uint8_t* stage = stage0 + (cidx & 1) * 4096;
+        if (lane == 0) tma_store_wait_read_1();  // the reduce that last read this staging tile is done
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+              make_uint4(v[cidx * 32 + ch * 4 + 0], v[cidx * 32 + ch * 4 + 1], v[cidx * 32 + ch * 4 + 2],
+                         v[cidx * 32 + ch * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_3d(&tmap_dq32, smem_u32(stage), cidx * 32, i * kTileM + dw * 32, static_cast<int>(bh));
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  } else {
+    // =========================================================================================
+    // P / dS warps: thread (r, half) owns key row r of the tile and the 64-query half `half`
+    // =========================================================================================
+    setmaxnreg_inc<144>();
+    const int half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int key = key0 + r;
+    const bool key_ok = key < p.Nkv;
+    const float c = p.scale_log2;
+
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+      const int i = i_begin + it;
+      const int par = it & 1;
+      const float* sL = sLD + (it & 1) * 256;
+      const float* sD = sL + 128;
+      const bool need_mask = (kCausal && i == j) || (key0 + kTileN > p.Nkv) || ((i + 1) * kTileM > p.Nq);
+
+      // ---- phase A: P^T = 2^(S^T c - L) for my 64 queries; 16-bit copy over the S^T columns
+      mbar_wait(bar_ld_full(it & 1), (it >> 1) & 1, 71);
+      mbar_wait(bar_s, par, 72);
+      tc_fence_after();
+      float pf[64];
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        const int qb = half * 64 + q2 * 32;  // first query (inside the tile) of this chunk
+        uint32_t sv[32];
+        tmem_ld_x32(tmem + lane_base + kColS + qb, sv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c, -sL[qb + e]));
+          if (need_mask) {
+            const int qrow = i * kTileM + qb + e;
+            const bool ok = key_ok && qrow < p.Nq && (!kCausal || key <= qrow);
+            pe = ok ? pe : 0.f;
+          }
+          pf[q2 * 32 + e] = pe;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = pack2<kBF16>(pf[q2 * 32 + 2 * e], pf[q2 * 32 + 2 * e + 1]);
+        tmem_st_x16(tmem + lane_base + kColS + half * 64 + q2 * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_ready);
+
+      // ---- phase B: dS^T = P^T o (dP^T - D); 16-bit copy over the dP^T columns (A of dK) and, as my row of the
+      // [key][query] shared-memory tile (A of dQ_i = dS K_j, MN-major)
+      mbar_wait(bar_dp, par, 73);
+      tc_fence_after();
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        const int qb = half * 64 + q2 * 32;
+        uint32_t dv[32];
+        tmem_ld_x32(tmem + lane_base + kColdP + qb, dv);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float d0 = pf[q2 * 32 + e] * (__uint_as_float(dv[e]) - sD[qb + e]);
+          const float d1 = pf[q2 * 32 + e + 1] * (__uint_as_float(dv[e + 1]) - sD[qb + e + 1]);
+          pk[e >> 1] = pack2<kBF16>(d0, d1);
+        }
+        tmem_st_x16(tmem + lane_base + kColdP + half * 64 + q2 * 16, pk);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(smem + L::kdS + sw128_offset_16bit(r, qb + ch * 8)) =
+              make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+      }
+      tmem_wait_st();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ds_ready);
+    }
+
+    // ---- epilogue: dV and scale * dK (TMEM lane = key row) -> 16 bit -> swizzled smem (the two Q buffers) -> TMA
+    // store.  The dQ commit of the last tile covers every MMA.  With no visible query tile (causal, keys beyond
+    // the last query) the gradients of this key tile are zero.
+    if (n_iter > 0) {
+      mbar_wait(bar_dq, (n_iter - 1) & 1, 74);
+      tc_fence_after();
+    }
+    uint8_t* st_dv = smem + L::kQ;
+    uint8_t* st_dk = smem + L::kQ + L::kTileBytes;
+#pragma unroll
+    for (int cidx = 0; cidx < kHalfD / 32; ++cidx) {
+      uint32_t a[32], k2[32];
+      if (n_iter > 0) {
+        tmem_ld_x32(tmem + lane_base + kColdV + half * kHalfD + cidx * 32, a);
+        tmem_ld_x32(tmem + lane_base + kColdK + half * kHalfD + cidx * 32, k2);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) a[e] = k2[e] = 0u;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 vv, kk;
+        vv.x = pack2<kBF16>(__uint_as_float(a[ch * 8 + 0]), __uint_as_float(a[ch * 8 + 1]));
+        vv.y = pack2<kBF16>(__uint_as_float(a[ch * 8 + 2]), __uint_as_float(a[ch * 8 + 3]));
+        vv.z = pack2<kBF16>(__uint_as_float(a[ch * 8 + 4]), __uint_as_float(a[ch * 8 + 5]));
+        vv.w = pack2<kBF16>(__uint_as_float(a[ch * 8 + 6]), __uint_as_float(a[ch * 8 + 7]));
+        kk.x = pack2<kBF16>(__uint_as_float(k2[ch * 8 + 0]) * p.scale, __uint_as_float(k2[ch * 8 + 1]) * p.scale);
+        kk.y = pack2<kBF16>(__uint_as_float(k2[ch * 8 + 2]) * p.scale, __uint_as_float(k2[ch * 8 + 3]) * p.scale);
+        kk.z = pack2<kBF16>(__uint_as_float(k2[ch * 8 + 4]) * p.scale, __uint_as_float(k2[ch * 8 + 5]) * p.scale);
+        kk.w = pack2<kBF16>(__uint_as_float(k2[ch * 8 + 6]) * p.scale, __uint_as_float(k2[ch * 8 + 7]) * p.scale);
+        const uint32_t off = sw128_offset_16bit(r, half * kHalfD + cidx * 32 + ch * 8);
+        *reinterpret_cast<uint4*>(st_dv + off) = vv;
+        *reinterpret_cast<uint4*>(st_dk + off) = kk;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (tid == 0) {
+#pragma unroll
+      for (int db = 0; db < kDBlocks; ++db) {
+        tma_store_4d(&tmap_dv, smem_u32(st_dv) + db * 16384, db * 64, key0, h, b);
+        tma_store_4d(&tmap_dk, smem_u32(st_dk) + db * 16384, db * 64, key0, h, b);
+      }
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fa

@@ -26,6 +26,7 @@
 #include "../../include/fa_fwd_sm100_test.h"
 #include "fa_bwd_simt.cuh"
 #include "fa_bwd_tc.cuh"
+#include "fa_bwd_ws.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
@@ -647,17 +648,18 @@ int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse
 // ---------------------------------------------------------------------------------------------
 struct BwdMaps {
   CUtensorMap q, k, v, d_o, dk, dv, dq;
+  CUtensorMap dq32;  // the same accumulator with a {32 columns, 32 rows} box (one per drain warp, fa_bwd_ws.cuh)
 };
 
 // 3-D fp32 map over the contiguous dq accumulator [B*H, Nq, DP]: box {32 columns = one 128-byte
 // swizzle row, 128 rows, 1}; rows >= Nq of a partial tile are clipped by the reduce.
-int make_map_dq(CUtensorMap* map, float* base, int BH, int Nq, int DP) {
+int make_map_dq(CUtensorMap* map, float* base, int BH, int Nq, int DP, int box_rows = 128) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return fail(FA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(DP), static_cast<cuuint64_t>(Nq),
                         static_cast<cuuint64_t>(BH)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(DP) * 4, static_cast<cuuint64_t>(Nq) * DP * 4};
-  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -686,10 +688,42 @@ int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int N
   return FA_OK;
 }
 
+template <int kDP, bool kBF16, bool kCausal>
+int launch_bwd_ws(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
+                  cudaStream_t stream) {
+  dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
+  auto kernel = fa::fa_bwd_ws_kernel<kDP, kBF16, kCausal>;
+  constexpr int smem = fa::BwdWsSmem<kDP>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, device);
+  if (rc) return rc;
+  kernel<<<grid, fa::kBwdWsThreads, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq32, bp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+// 0 = automatic (the pipelined kernel fa_bwd_ws.cuh), 1 = the serial kernel fa_bwd_tc.cuh, 2 = fa_bwd_ws.cuh
+std::atomic<int> g_bwd_kernel{0};
+
 int dispatch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int D, int dtype,
                     int causal, int device, cudaStream_t stream) {
   const bool bf = dtype == FA_DTYPE_BF16;
   const bool ca = causal != 0;
+  if (g_bwd_kernel.load() != 1) {
+#define FA_BWD_WS_DISPATCH(DP)                                                                 \
+  do {                                                                                         \
+    if (bf) {                                                                                  \
+      if (ca) return launch_bwd_ws<DP, true, true>(m, bp, B, H, Nkv, device, stream);          \
+      return launch_bwd_ws<DP, true, false>(m, bp, B, H, Nkv, device, stream);                 \
+    }                                                                                          \
+    if (ca) return launch_bwd_ws<DP, false, true>(m, bp, B, H, Nkv, device, stream);           \
+    return launch_bwd_ws<DP, false, false>(m, bp, B, H, Nkv, device, stream);                  \
+  } while (0)
+    if (D <= 64) FA_BWD_WS_DISPATCH(64);
+    FA_BWD_WS_DISPATCH(128);
+#undef FA_BWD_WS_DISPATCH
+  }
 #define FA_BWD_DISPATCH(DP)                                                                    \
   do {                                                                                         \
     if (bf) {                                                                                  \
@@ -741,6 +775,7 @@ struct BwdPlanCache {
     if ((rc = make_map(&pl.m.dk, key.ptr[4], B, H, Nkv, D, key.st[4], dt, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.m.dv, key.ptr[5], B, H, Nkv, D, key.st[5], dt, fa::kTileN))) return rc;
     if ((rc = make_map_dq(&pl.m.dq, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D))) return rc;
+    if ((rc = make_map_dq(&pl.m.dq32, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D, 32))) return rc;
     if (plans.size() < kCap) {
       plans.push_back(pl);
     } else {
@@ -1078,6 +1113,8 @@ int fa_abi_version(void) { return FA_ABI_VERSION; }
 const char* fa_last_error(void) { return g_err.c_str(); }
 
 uint64_t fa_launch_count(void) { return g_launches.load(); }
+
+int fa_set_bwd_kernel(int kernel) { return g_bwd_kernel.exchange(kernel); }
 
 int fa_set_kernel(int kernel) {
   if (kernel < FA_KERNEL_AUTO || kernel > FA_KERNEL_WS3 || kernel == 3 || kernel == 8) return -FA_ERR_INVALID_ARG;

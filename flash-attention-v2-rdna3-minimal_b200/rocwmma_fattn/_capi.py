@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = (
     "fa_host_plan_chunks",
 )
 TEST_HOOK_SYMBOLS = (
+    "fa_set_bwd_kernel",
     "fa_set_kernel",
     "fa_set_pdl",
     "fa_set_wide_pairs",
@@ -104,6 +105,8 @@ def _open() -> ctypes.CDLL:
     lib.fa_set_kernel.restype = i
     lib.fa_set_pdl.argtypes = [i]
     lib.fa_set_pdl.restype = i
+    lib.fa_set_bwd_kernel.argtypes = [i]
+    lib.fa_set_bwd_kernel.restype = i
     lib.fa_launch_count.argtypes = []
     lib.fa_launch_count.restype = ctypes.c_uint64
     lib.fa_umma_selftest.argtypes = [vp, vp, vp, i, i, ctypes.c_uint32, ctypes.c_uint32, vp]
@@ -176,6 +179,14 @@ def set_kernel(kernel: int) -> int:
     if prev < 0:
         raise ValueError(f"unknown kernel selector {kernel}")
     return prev
+
+
+FA_BWD_KERNEL_AUTO, FA_BWD_KERNEL_TC, FA_BWD_KERNEL_WS = 0, 1, 2
+
+
+def set_bwd_kernel(kernel: int) -> int:
+    """Backward kernel for head dims <= 128 (test hook): 0 auto, 1 serial (fa_bwd_tc), 2 pipelined (fa_bwd_ws)."""
+    return int(lib.fa_set_bwd_kernel(int(kernel)))
 
 
 def set_pdl(enable: bool) -> bool:

@@ -29,6 +29,10 @@ int fa_set_pdl(int enable);
  * heuristic.  Test / benchmarking hook.  Returns the previous setting. */
 int fa_set_kernel(int kernel);
 
+/* Backward kernel for head dims <= 128: 0 = automatic (the pipelined, warp-specialised kernel fa_bwd_ws.cuh),
+ * 1 = the serial kernel fa_bwd_tc.cuh (round 1), 2 = fa_bwd_ws.cuh.  Returns the previous setting. */
+int fa_set_bwd_kernel(int kernel);
+
 /*
  * UMMA / TMA / TMEM self-test: computes one 128x128x128 product through the same operand paths the
  * attention kernels use (mode 0: A.B^T both K-major; 1: A.B with B MN-major; 2: A from TMEM;

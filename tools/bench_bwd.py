@@ -16,6 +16,8 @@ from rocwmma_fattn.FlashAttn import flash_attn_wmma
 
 
 ns = [int(x) for x in sys.argv[1:]] or [1024, 4096, 16384]
+# FA_BWD=tc (serial kernel, round 1) | ws (pipelined kernel) | unset (library default)
+_capi.set_bwd_kernel({"tc": _capi.FA_BWD_KERNEL_TC, "ws": _capi.FA_BWD_KERNEL_WS}.get(os.environ.get("FA_BWD", ""), 0))
 H, D = 16, 128
 torch.manual_seed(0)
 res = {}
@@ -51,6 +53,6 @@ for dt_name, dt in (("f16", torch.float16),) if os.environ.get("FA_BWD_QUICK") e
             res[f"{dt_name}_{'causal' if causal else 'full'}_n{n}"] = {
                 "ms": round(best, 4), "tflops": round(fl / best / 1e9, 1)}
             del keep, g
-print(os.environ.get("FA_BWD", "tc1"), json.dumps({k: v["tflops"] for k, v in res.items()}))
+print(os.environ.get("FA_BWD", "default"), json.dumps({k: v["tflops"] for k, v in res.items()}))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_bwd.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"bench_bwd_{os.environ.get('FA_BWD', 'default')}.json"), "w"), indent=1)
