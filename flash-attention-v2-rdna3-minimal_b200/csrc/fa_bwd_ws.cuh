@@ -30,6 +30,9 @@
 namespace fa {
 
 constexpr int kBwdWsThreads = 512;
+#ifndef FA_BWD_EXP_NO_LD
+#define FA_BWD_EXP_NO_LD 0
+#endif
 
 template <int kDP>
 struct BwdWsSmem {
@@ -82,6 +85,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t bar_ds_ready = smem_u32(&bars[12]);                           // 8 warps: dS^T in TMEM, dS in smem
   const uint32_t bar_dq = smem_u32(&bars[13]);                                 // commit: dQ_i ready (all earlier MMAs done)
   const uint32_t bar_drained = smem_u32(&bars[14]);                            // 4 warps: dQ_i is in registers
+  auto bar_ld_free = [&](int b_) { return smem_u32(&bars[15 + b_]); };         // 8 warps: L / D vectors of tile i read
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -110,6 +114,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_q_full(i), 1);
       mbar_init(bar_ld_full(i), 32);
       mbar_init(bar_q_free(i), 1);
+      mbar_init(bar_ld_free(i), 8);
     }
     mbar_init(bar_do_full, 1);
     mbar_init(bar_do_free, 1);
@@ -264,8 +269,9 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           if (it + 2 < n_iter) {
             if (lane == 0) {
-              mbar_wait(bar_q_free(it & 1), (it >> 1) & 1, 69);  // dK(i) done: Q buffer and its L / D vectors are free
+              mbar_wait(bar_q_free(it & 1), (it >> 1) & 1, 69);  // dK(i) done with the Q buffer
               load_q(it + 2);
+              mbar_wait(bar_ld_free(it & 1), (it >> 1) & 1, 75);  // the P / dS warps have read its L / D vectors
             }
             __syncwarp();
             stage_ld(it + 2);
@@ -334,6 +340,11 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int par = it & 1;
       const float* sL = sLD + (it & 1) * 256;
       const float* sD = sL + 128;
+#if FA_BWD_EXP_NO_LD  // timing experiment only (wrong results): what do the broadcast reads of L / D cost?
+#define FA_LD_IDX(x) (qb)
+#else
+#define FA_LD_IDX(x) (x)
+#endif
       const bool need_mask = (kCausal && i == j) || (key0 + kTileN > p.Nkv) || ((i + 1) * kTileM > p.Nq);
 
       // ---- phase A: P^T = 2^(S^T c - L) for my 64 queries; 16-bit copy over the S^T columns
@@ -349,7 +360,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c, -sL[qb + e]));
+          float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c, -sL[FA_LD_IDX(qb + e)]));
           if (need_mask) {
             const int qrow = i * kTileM + qb + e;
             const bool ok = key_ok && qrow < p.Nq && (!kCausal || key <= qrow);
@@ -380,8 +391,8 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float d0 = pf[q2 * 32 + e] * (__uint_as_float(dv[e]) - sD[qb + e]);
-          const float d1 = pf[q2 * 32 + e + 1] * (__uint_as_float(dv[e + 1]) - sD[qb + e + 1]);
+          const float d0 = pf[q2 * 32 + e] * (__uint_as_float(dv[e]) - sD[FA_LD_IDX(qb + e)]);
+          const float d1 = pf[q2 * 32 + e + 1] * (__uint_as_float(dv[e + 1]) - sD[FA_LD_IDX(qb + e + 1)]);
           pk[e >> 1] = pack2<kBF16>(d0, d1);
         }
         tmem_st_x16(tmem + lane_base + kColdP + half * 64 + q2 * 16, pk);
@@ -394,7 +405,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ds_ready);
+      if (lane == 0) {
+        mbar_arrive(bar_ds_ready);
+        mbar_arrive(bar_ld_free(it & 1));
+      }
     }
 
     // ---- epilogue: dV and scale * dK (TMEM lane = key row) -> 16 bit -> swizzled smem (the two Q buffers) -> TMA

@@ -79,10 +79,20 @@ SHAPES = [
 ]
 
 
+@pytest.fixture
+def bwd_kernel(request):
+    """Force a backward kernel for one test (fa_set_bwd_kernel, test-hook header) and restore the default."""
+    prev = _capi.set_bwd_kernel(request.param)
+    yield request.param
+    _capi.set_bwd_kernel(prev)
+
+
+@pytest.mark.parametrize("bwd_kernel", [_capi.FA_BWD_KERNEL_WS, _capi.FA_BWD_KERNEL_TC], indirect=True,
+                         ids=["pipelined", "serial"])
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("dtype", [F16, BF16])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_backward_matches_fp32_autograd(shape, dtype, causal):
+def test_backward_matches_fp32_autograd(shape, dtype, causal, bwd_kernel):
     B, H, Nq, Nkv, D = shape
     q, k, v = orc.make_inputs(B, H, Nq, Nkv, D, dtype, seed=sum(shape) + 7 * int(causal))
     g = torch.Generator().manual_seed(99 + sum(shape))
@@ -94,6 +104,27 @@ def test_backward_matches_fp32_autograd(shape, dtype, causal):
     # the query rows, i.e. the 16-bit rounding of the stored O (any FA2 backward has it)
     atol = 2e-4 if Nkv == 1 else 0.0
     assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal}", atol)
+
+
+def test_default_backward_kernel_is_the_pipelined_one_and_agrees_with_the_serial_kernel():
+    """dK and dV do not depend on any summation order across CTAs, so the two kernels must agree to rounding of
+    their 16-bit P / dS intermediates; dQ is an fp32 reduce-add in both."""
+    assert _capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_AUTO) == _capi.FA_BWD_KERNEL_AUTO  # nothing forced by default
+    B, H, N, D = 2, 4, 1024, 128
+    q, k, v = orc.make_inputs(B, H, N, N, D, F16, seed=5)
+    d_o = torch.rand((B, H, N, D), generator=torch.Generator().manual_seed(6)).to(F16)
+    args = (q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV))
+    n0 = _capi.launch_count()
+    auto = grads(*args, True)[1:]
+    assert _capi.launch_count() - n0 == 4  # forward, delta pre-pass, main kernel, dQ conversion
+    prev = _capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_TC)
+    try:
+        serial = grads(*args, True)[1:]
+    finally:
+        _capi.set_bwd_kernel(prev)
+    for nm, a, b in zip(("dq", "dk", "dv"), auto, serial):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 2e-3 * max(1e-3, b.float().abs().max().item()) + 1e-5, f"{nm}: kernels disagree by {err:.3e}"
 
 
 def test_backward_randn_inputs_and_custom_scale():
