@@ -691,7 +691,11 @@ int launch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int N
 template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_ws(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
                   cudaStream_t stream) {
-  dim3 grid((Nkv + fa::kTileN - 1) / fa::kTileN, H, B);
+  const unsigned n_j = static_cast<unsigned>((Nkv + fa::kTileN - 1) / fa::kTileN);
+  // causal: longest key tile first across heads (1-D grid, see the kernel) while the launch is at most ten rounds
+  const unsigned ctas = n_j * static_cast<unsigned>(H) * static_cast<unsigned>(B);
+  const dim3 grid = (kCausal && ctas <= 10u * 148u) ? dim3(ctas, 1, 1)
+                                                    : dim3(n_j, static_cast<unsigned>(H), static_cast<unsigned>(B));
   auto kernel = fa::fa_bwd_ws_kernel<kDP, kBF16, kCausal>;
   constexpr int smem = fa::BwdWsSmem<kDP>::kTotal;
   static std::atomic<uint64_t> configured{0};
