@@ -725,18 +725,22 @@ def main():
         # TFLOPS = 2.5 x forward FLOPs / t (bench_with_sdpa.py:39-40)
         from rocwmma_fattn.FlashAttn import flash_attn_wmma
 
-        bwd = {}
-        for n in (4096, 16384):
-            q, k, v = pools[n][0]
-            d_o = torch.rand_like(q)
-            _, qp, kp, vp, o_pad, lse = flash_attn_wmma.forward(q, k, v, 64, 128, False, D ** -0.5, False)
+        for causal_b, name_b in ((False, "f16_backward_noncausal"), (True, "f16_backward_causal")):
+            bwd = {}
+            for n in (1024, 2048, 4096, 8192, 16384):
+                q, k, v = pools[n][0]
+                d_o = torch.rand_like(q)
+                _, qp, kp, vp, o_pad, lse = flash_attn_wmma.forward(q, k, v, 64, 128, causal_b, D ** -0.5, False)
 
-            def bfn(*_a, n=n, qp=qp, kp=kp, vp=vp, o_pad=o_pad, d_o=d_o, lse=lse):
-                return flash_attn_wmma.backward(qp, kp, vp, o_pad, d_o, lse, n, n, D, 128, 128, False, D ** -0.5, False)
+                def bfn(*_a, n=n, qp=qp, kp=kp, vp=vp, o_pad=o_pad, d_o=d_o, lse=lse, cb=causal_b):
+                    return flash_attn_wmma.backward(qp, kp, vp, o_pad, d_o, lse, n, n, D, 128, 128, cb, D ** -0.5, False)
 
-            ms = time_variant(bfn, [(None, None, None)] * 2, False, 2.5 * flops(1, H, n, D))
-            bwd[str(n)] = {"ms": round(ms, 5), "tflops": round(2.5 * flops(1, H, n, D) / (ms * 1e-3) / 1e12, 2)}
-        extras["f16_backward_noncausal"] = bwd
+                fl = 2.5 * flops(1, H, n, D, causal_b)
+                ms = time_variant(bfn, [(None, None, None)] * 2, False, fl)
+                bwd[str(n)] = {"ms": round(ms, 5), "tflops": round(fl / (ms * 1e-3) / 1e12, 2),
+                               "frac_of_peak": round(fl / (ms * 1e-3) / 1e12 / peaks["tflops"], 4)}
+            bwd["kernel"] = "fa_bwd_ws_kernel (pipelined, warp-specialised) + delta pre-pass + dQ conversion; 3 launches per call"
+            extras[name_b] = bwd
 
         # the reference's head-dim sweep (bench_with_sdpa.py:259-283: D = 16 i at N = 4096) and the SD head dims at
         # N = 16384: ws3 at D <= 64, ws/sk up to 128, wide / wide2 (one Q tile per CTA, CTA pairs above 192) above
