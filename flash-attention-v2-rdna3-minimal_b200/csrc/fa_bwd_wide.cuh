@@ -1,0 +1,308 @@
+// tcgen05 backward for head dims 129..256 ("bwd wide", round 2).
+//
+// fa_bwd_ws.cuh keeps S^T, dP^T, dV and dK in tensor memory at once (256 + 2 D columns) and K, V, 2 x Q, dO in shared
+// memory (5 x 128 x D x 2 bytes): neither fits above head dim 128, and until this file those head dims (the 160 of
+// SD 1.5 the reference serves by padding, kernel_fp16.cu:900) ran the CUDA-core kernels of fa_bwd_simt.cuh at under
+// 1 TFLOP/s.  Here the three gradients are computed by THREE launches of one kernel, each of which holds a single
+// 128 x D accumulator in tensor memory and recomputes the scores it needs (8 GEMMs instead of 5; no fp32 dQ buffer, no
+// atomics, no conversion pass):
+//
+//   mode dV : CTA = 128 keys.   per 64-query tile:  S^T = K Q^T                 P^T        ->  dV += P^T dO
+//   mode dK : CTA = 128 keys.   per 64-query tile:  S^T = K Q^T, dP^T = V dO^T  dS^T       ->  dK += dS^T Q
+//   mode dQ : CTA = 128 queries per 64-key tile:    S = Q K^T,   dP = dO V^T    dS         ->  dQ += dS K
+//
+// with P = 2^(S c - L), dS = P o (dP - D) (kernel_fp16.cu:698-737).  In every mode the CTA's own 128 rows ("resident":
+// K,V or Q,dO) are TMEM lanes, the other operand streams through shared memory in 64-row tiles, the 16-bit P / dS goes
+// back to tensor memory and feeds the output product as its A operand (tcgen05.mma TS form), and the streamed tile is
+// the MN-major B operand of that product.  The score products are M=128, N=64, K=D; the output product M=128, N=D, K=64.
+// Mode dQ is mode dK with the roles of (Q,dO) and (K,V) exchanged; its L_i, D_i are per-lane scalars, in the other two
+// modes they are vectors over the 64 streamed queries (staged in shared memory, read as broadcasts).
+//
+// This is the serial arrangement (one thread issues TMA and MMA, 256 threads do the P / dS pass between two CTA
+// barriers; the streamed tiles are double-buffered where shared memory allows): a first tensor-core version, ~500x
+// the CUDA-core kernels it replaces, not yet pipelined like fa_bwd_ws.cuh.
+//
+// TMEM: scores [0,64), dP [64,128), accumulator [128,128+D), 16-bit P/dS [384,416).
+#pragma once
+#include "fa_bwd_tc.cuh"
+
+namespace fa {
+
+constexpr int kBwdWideDV = 0, kBwdWideDK = 1, kBwdWideDQ = 2;
+constexpr int kBwdWideThreads = 256;
+constexpr int kWideT = 64;  // rows of a streamed tile
+
+template <int kDP, int kMode>
+struct BwdWideSmem {
+  static constexpr int kResBytes = kTileM * kDP * 2;  // one resident tile [128][kDP]
+  static constexpr int kStrBytes = kWideT * kDP * 2;  // one streamed tile [64][kDP]
+  static constexpr int kNumRes = (kMode == kBwdWideDV) ? 1 : 2;
+  static constexpr int kStages = (kNumRes * kResBytes + 2 * 2 * kStrBytes <= 222 * 1024) ? 2 : 1;
+  static constexpr int kRes = 0;
+  static constexpr int kStr = kNumRes * kResBytes;            // [stage][2][kStrBytes]
+  static constexpr int kLD = kStr + kStages * 2 * kStrBytes;  // float [2 (L, D)][64] (vector modes)
+  static constexpr int kBars = kLD + 2 * 64 * 4;
+  static constexpr int kTotal = kBars + 128 + 1024;           // + alignment slack
+};
+
+struct BwdWideParams {
+  const float* lse;    // [B,H,Nq] base-2 log-sum-exp of the scaled scores (forward output)
+  const float* delta;  // [B,H,Nq] rowsum(dO o O), fp32 (fa_bwd_delta_kernel)
+  int Nq, Nkv, H;
+  float scale_log2;    // scale * log2(e)
+  float out_scale;     // 1 (dV) or scale (dK, dQ)
+};
+
+template <int kDP, bool kBF16, bool kCausal, int kMode>
+__global__ void __launch_bounds__(kBwdWideThreads, 1)
+fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK) | Q (dQ), box {64, 128}
+                   const __grid_constant__ CUtensorMap tmap_res2,  // V (dK) | dO (dQ); unused in mode dV
+                   const __grid_constant__ CUtensorMap tmap_str1,  // Q (dV, dK) | K (dQ), box {64, 64}
+                   const __grid_constant__ CUtensorMap tmap_str2,  // dO (dV, dK) | V (dQ)
+                   const __grid_constant__ CUtensorMap tmap_out,   // dV | dK | dQ, box {64, 128}
+                   const BwdWideParams p) {
+  using L = BwdWideSmem<kDP, kMode>;
+  constexpr int kS = L::kStages;
+  constexpr int kDBlocks = kDP / 64;
+  constexpr int kKSteps = kDP / 16;  // contraction over the head dim (scores)
+  constexpr bool kVecLD = (kMode != kBwdWideDQ);  // L, D are vectors over the streamed queries
+  constexpr uint32_t kColS = 0, kColP = 64, kColAcc = 128, kColA = 384;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t sRes1 = smem_u32(smem + L::kRes);
+  const uint32_t sRes2 = sRes1 + L::kResBytes;  // (not present in mode dV)
+  const uint32_t sStr = smem_u32(smem + L::kStr);
+  float* sLD = reinterpret_cast<float*>(smem + L::kLD);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBars + 64);
+  const uint32_t bar_res = smem_u32(&bars[0]);                          // tx: resident tiles
+  auto bar_str = [&](int s) { return smem_u32(&bars[1 + s]); };         // tx: streamed tile pair of a stage
+  const uint32_t bar_mma1 = smem_u32(&bars[3]);                         // commit: scores ready
+  const uint32_t bar_mma2 = smem_u32(&bars[4]);                         // commit: output product done
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int half = warp >> 2;             // which 32 of the 64 streamed columns this thread owns
+  const int r = (warp & 3) * 32 + lane;   // row inside the resident tile = TMEM lane
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const int rt = blockIdx.x;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row0 = rt * kTileM;
+  const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+
+  // streamed-tile range of this CTA
+  const int n_cols = kVecLD ? p.Nq : p.Nkv;
+  const int n_ct = (n_cols + kWideT - 1) / kWideT;
+  int ct0 = 0, ct1 = n_ct;
+  if (kCausal) {
+    if (kVecLD) ct0 = min(n_ct, row0 / kWideT);                         // queries >= the first key of the tile
+    else ct1 = min(n_ct, (row0 + kTileM - 1) / kWideT + 1);             // keys <= the last query of the tile
+  }
+  const int n_iter = ct1 - ct0;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_res1);
+    tma_prefetch_desc(&tmap_res2);
+    tma_prefetch_desc(&tmap_str1);
+    tma_prefetch_desc(&tmap_str2);
+    tma_prefetch_desc(&tmap_out);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  auto load_str = [&](int it) {  // streamed tile pair of iteration `it` -> stage it % kS
+    const int s = it % kS;
+    const uint32_t dst = sStr + s * 2 * L::kStrBytes;
+    mbar_arrive_expect_tx(bar_str(s), 2 * L::kStrBytes);
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) {
+      tma_load_4d(dst + db * 8192, &tmap_str1, bar_str(s), db * 64, (ct0 + it) * kWideT, h, b);
+      tma_load_4d(dst + L::kStrBytes + db * 8192, &tmap_str2, bar_str(s), db * 64, (ct0 + it) * kWideT, h, b);
+    }
+  };
+
+  if (tid == 0 && n_iter > 0) {
+    mbar_arrive_expect_tx(bar_res, L::kNumRes * L::kResBytes);
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) {
+      tma_load_4d(sRes1 + db * 16384, &tmap_res1, bar_res, db * 64, row0, h, b);
+      if (L::kNumRes == 2) tma_load_4d(sRes2 + db * 16384, &tmap_res2, bar_res, db * 64, row0, h, b);
+    }
+    load_str(0);
+    if (kS == 2 && n_iter > 1) load_str(1);
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_f16(kTileM, kWideT, kBF16, false, false);  // scores: M=128, N=64
+  constexpr uint32_t idesc_o = make_idesc_f16(kTileM, kDP, kBF16, false, true);      // output: N=kDP, B MN-major
+  const float c = p.scale_log2;
+  const int row_abs = row0 + r;
+
+  // L / D: per-lane scalars (mode dQ) or, one streamed tile ahead, the value this thread will stage (vector modes)
+  float l_lane = 0.f, d_lane = 0.f, ld_next = 0.f;
+  const float* ld_src = (tid < 64) ? p.lse : p.delta;
+  if (!kVecLD) {
+    if (row_abs < p.Nq) {
+      l_lane = p.lse[bh * p.Nq + row_abs];
+      d_lane = p.delta[bh * p.Nq + row_abs];
+    }
+  } else if (tid < 128 && n_iter > 0) {
+    const int q = ct0 * kWideT + (tid & 63);
+    ld_next = (q < p.Nq) ? ld_src[bh * p.Nq + q] : 0.f;
+  }
+
+  int waited2 = 0;  // bar_mma2 phases thread 0 has observed (it must observe every phase in order)
+#pragma unroll 1
+  for (int it = 0; it < n_iter; ++it) {
+    const int ct = ct0 + it;
+    const int s = it % kS;
+    if (kVecLD && tid < 128) {
+      sLD[tid] = ld_next;
+      if (it + 1 < n_iter) {
+        const int q = (ct + 1) * kWideT + (tid & 63);
+        ld_next = (q < p.Nq) ? ld_src[bh * p.Nq + q] : 0.f;
+      }
+    }
+    __syncthreads();  // (A) L / D of this tile visible; every thread is done with the previous tile's scores
+
+    if (tid == 0) {
+      if (it == 0) mbar_wait(bar_res, 0, 80);
+      mbar_wait(bar_str(s), (it / kS) & 1, 81);
+      tc_fence_after();
+      const uint32_t t1 = sStr + s * 2 * L::kStrBytes, t2 = t1 + L::kStrBytes;
+#pragma unroll
+      for (int k = 0; k < kKSteps; ++k) {
+        umma_ss(tmem + kColS, make_smem_desc_sw128(sRes1 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                make_smem_desc_sw128(t1 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+      }
+      if (kMode != kBwdWideDV) {
+#pragma unroll
+        for (int k = 0; k < kKSteps; ++k) {
+          umma_ss(tmem + kColP, make_smem_desc_sw128(sRes2 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(t2 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+        }
+      }
+      tc_commit(bar_mma1);
+      // two stages: the tile of iteration it+1 goes where iteration it-1's was, once its output product is done
+      if (kS == 2 && it >= 1 && it + 1 < n_iter) {
+        mbar_wait(bar_mma2, waited2 & 1, 82);
+        ++waited2;
+        load_str(it + 1);
+      }
+    }
+
+    // ---- P (and dS) for my 32 columns of my row
+    const bool need_mask = (kCausal && (kVecLD ? (ct * kWideT < row0 + kTileM) : ((ct + 1) * kWideT > row0))) ||
+                           ((ct + 1) * kWideT > n_cols) || (row0 + kTileM > (kVecLD ? p.Nkv : p.Nq));
+    mbar_wait(bar_mma1, it & 1, 83);
+    tc_fence_after();
+    {
+      uint32_t sv[32], dv[32];
+      tmem_ld_x32(tmem + lane_base + kColS + half * 32, sv);
+      if (kMode != kBwdWideDV) tmem_ld_x32(tmem + lane_base + kColP + half * 32, dv);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float val[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int col = half * 32 + e + u;
+          const float lq = kVecLD ? sLD[col] : l_lane;
+          float pe = ex2_approx(fmaf(__uint_as_float(sv[e + u]), c, -lq));
+          if (need_mask) {
+            const int col_abs = ct * kWideT + col;
+            const int key = kVecLD ? row_abs : col_abs;
+            const int qrow = kVecLD ? col_abs : row_abs;
+            const bool ok = key < p.Nkv && qrow < p.Nq && (!kCausal || key <= qrow);
+            pe = ok ? pe : 0.f;
+          }
+          if (kMode == kBwdWideDV) {
+            val[u] = pe;
+          } else {
+            const float dq_ = kVecLD ? sLD[64 + col] : d_lane;
+            val[u] = pe * (__uint_as_float(dv[e + u]) - dq_);
+          }
+        }
+        pk[e >> 1] = pack2<kBF16>(val[0], val[1]);
+      }
+      tmem_st_x16(tmem + lane_base + kColA + half * 16, pk);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();  // (B) the 16-bit tile is complete
+
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t t_out = sStr + s * 2 * L::kStrBytes + ((kMode == kBwdWideDV) ? L::kStrBytes : 0);
+#pragma unroll
+      for (int ks = 0; ks < kWideT / 16; ++ks) {  // contraction over the 64 streamed rows
+        umma_ts(tmem + kColAcc, tmem + kColA + ks * 8, make_smem_desc_sw128(t_out + ks * 2048, 8192, 1024), idesc_o,
+                (it > 0) || (ks > 0));
+      }
+      tc_commit(bar_mma2);
+      if (kS == 1 && it + 1 < n_iter) {  // one stage: the next tile pair can only be fetched now
+        mbar_wait(bar_mma2, waited2 & 1, 84);
+        ++waited2;
+        load_str(it + 1);
+      }
+    }
+  }
+
+  // ---- epilogue: accumulator -> x out_scale -> 16 bit -> swizzled smem (the first resident tile) -> TMA store.
+  // With no visible streamed tile (causal, keys beyond the last query) the gradients of this tile are zero.
+  if (tid == 0) {
+    while (waited2 < n_iter) {
+      mbar_wait(bar_mma2, waited2 & 1, 85);
+      ++waited2;
+    }
+  }
+  __syncthreads();
+  tc_fence_after();
+  uint8_t* stage = smem + L::kRes;
+  constexpr int kHalfD = kDP / 2;
+#pragma unroll 1
+  for (int cidx = 0; cidx < kHalfD / 32; ++cidx) {
+    uint32_t a[32];
+    if (n_iter > 0) {
+      tmem_ld_x32(tmem + lane_base + kColAcc + half * kHalfD + cidx * 32, a);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a[e] = 0u;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint4 vv;
+      vv.x = pack2<kBF16>(__uint_as_float(a[ch * 8 + 0]) * p.out_scale, __uint_as_float(a[ch * 8 + 1]) * p.out_scale);
+      vv.y = pack2<kBF16>(__uint_as_float(a[ch * 8 + 2]) * p.out_scale, __uint_as_float(a[ch * 8 + 3]) * p.out_scale);
+      vv.z = pack2<kBF16>(__uint_as_float(a[ch * 8 + 4]) * p.out_scale, __uint_as_float(a[ch * 8 + 5]) * p.out_scale);
+      vv.w = pack2<kBF16>(__uint_as_float(a[ch * 8 + 6]) * p.out_scale, __uint_as_float(a[ch * 8 + 7]) * p.out_scale);
+      *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kHalfD + cidx * 32 + ch * 8)) = vv;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int db = 0; db < kDBlocks; ++db) tma_store_4d(&tmap_out, smem_u32(stage) + db * 16384, db * 64, row0, h, b);
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fa

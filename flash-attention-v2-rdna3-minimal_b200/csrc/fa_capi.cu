@@ -27,6 +27,7 @@
 #include "fa_bwd_simt.cuh"
 #include "fa_bwd_tc.cuh"
 #include "fa_bwd_ws.cuh"
+#include "fa_bwd_wide.cuh"
 #include "fa_fwd_simt.cuh"
 #include "fa_fwd_tc.cuh"
 #include "fa_fwd_ws.cuh"
@@ -649,6 +650,8 @@ int launch_simt(const void* q, const void* k, const void* v, void* o, float* lse
 struct BwdMaps {
   CUtensorMap q, k, v, d_o, dk, dv, dq;
   CUtensorMap dq32;  // the same accumulator with a {32 columns, 32 rows} box (one per drain warp, fa_bwd_ws.cuh)
+  // head dims 129..256 (fa_bwd_wide.cuh): the inputs again with 64-row boxes (streamed tiles) and dQ as a 16-bit output
+  CUtensorMap q64, k64, v64, do64, dq16;
 };
 
 // 3-D fp32 map over the contiguous dq accumulator [B*H, Nq, DP]: box {32 columns = one 128-byte
@@ -742,12 +745,63 @@ int dispatch_bwd_tc(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int
 #undef FA_BWD_DISPATCH
 }
 
+template <int kDP, bool kBF16, bool kCausal, int kMode>
+int launch_bwd_wide_mode(const BwdMaps& m, const fa::BwdWideParams& wp, int B, int H, int n_rows, int device,
+                         cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>((n_rows + fa::kTileM - 1) / fa::kTileM), static_cast<unsigned>(H),
+            static_cast<unsigned>(B));
+  auto kernel = fa::fa_bwd_wide_kernel<kDP, kBF16, kCausal, kMode>;
+  constexpr int smem = fa::BwdWideSmem<kDP, kMode>::kTotal;
+  static std::atomic<uint64_t> configured{0};
+  int rc = set_smem(kernel, smem, &configured, device);
+  if (rc) return rc;
+  if (kMode == fa::kBwdWideDV)
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.k, m.q64, m.do64, m.dv, wp);
+  else if (kMode == fa::kBwdWideDK)
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.v, m.q64, m.do64, m.dk, wp);
+  else
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.q, m.d_o, m.k64, m.v64, m.dq16, wp);
+  FA_CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+// head dims 129..256: dV, dK and dQ by three launches of fa_bwd_wide_kernel (see fa_bwd_wide.cuh)
+template <int kDP, bool kBF16, bool kCausal>
+int launch_bwd_wide(const BwdMaps& m, fa::BwdWideParams wp, int B, int H, int Nq, int Nkv, float scale, int device,
+                    cudaStream_t stream) {
+  int rc;
+  wp.out_scale = 1.f;
+  if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDV>(m, wp, B, H, Nkv, device, stream))) return rc;
+  wp.out_scale = scale;
+  if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDK>(m, wp, B, H, Nkv, device, stream))) return rc;
+  return launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDQ>(m, wp, B, H, Nq, device, stream);
+}
+
+int dispatch_bwd_wide(const BwdMaps& m, const fa::BwdWideParams& wp, int B, int H, int Nq, int Nkv, int D, int dtype,
+                      int causal, float scale, int device, cudaStream_t stream) {
+  const bool bf = dtype == FA_DTYPE_BF16;
+  const bool ca = causal != 0;
+#define FA_BWD_WIDE_DISPATCH(DP)                                                                         \
+  do {                                                                                                   \
+    if (bf) {                                                                                            \
+      if (ca) return launch_bwd_wide<DP, true, true>(m, wp, B, H, Nq, Nkv, scale, device, stream);       \
+      return launch_bwd_wide<DP, true, false>(m, wp, B, H, Nq, Nkv, scale, device, stream);              \
+    }                                                                                                    \
+    if (ca) return launch_bwd_wide<DP, false, true>(m, wp, B, H, Nq, Nkv, scale, device, stream);        \
+    return launch_bwd_wide<DP, false, false>(m, wp, B, H, Nq, Nkv, scale, device, stream);               \
+  } while (0)
+  if (D <= 192) FA_BWD_WIDE_DISPATCH(192);
+  FA_BWD_WIDE_DISPATCH(256);
+#undef FA_BWD_WIDE_DISPATCH
+}
+
 // Tensor maps of one backward call, cached like the forward's Plan (encoding seven maps costs ~10 us of
 // host time per call; training loops present the same buffers again and again through the caching allocator).
 struct BwdPlan {
-  const void* ptr[7];
+  const void* ptr[8];  // q, k, v, dO, dK, dV, dq accumulator (head dims <= 128), dQ (head dims > 128)
   int B, H, Nq, Nkv, D, dtype, device;
-  int64_t st[6][4];
+  int64_t st[7][4];
   BwdMaps m;
   uint64_t stamp;
 };
@@ -778,8 +832,16 @@ struct BwdPlanCache {
     if ((rc = make_map(&pl.m.d_o, key.ptr[3], B, H, Nq, D, key.st[3], dt, fa::kTileM))) return rc;
     if ((rc = make_map(&pl.m.dk, key.ptr[4], B, H, Nkv, D, key.st[4], dt, fa::kTileN))) return rc;
     if ((rc = make_map(&pl.m.dv, key.ptr[5], B, H, Nkv, D, key.st[5], dt, fa::kTileN))) return rc;
-    if ((rc = make_map_dq(&pl.m.dq, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D))) return rc;
-    if ((rc = make_map_dq(&pl.m.dq32, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D, 32))) return rc;
+    if (D <= 128) {
+      if ((rc = make_map_dq(&pl.m.dq, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D))) return rc;
+      if ((rc = make_map_dq(&pl.m.dq32, static_cast<float*>(const_cast<void*>(key.ptr[6])), B * H, Nq, D, 32))) return rc;
+    } else {
+      if ((rc = make_map(&pl.m.q64, key.ptr[0], B, H, Nq, D, key.st[0], dt, fa::kWideT))) return rc;
+      if ((rc = make_map(&pl.m.k64, key.ptr[1], B, H, Nkv, D, key.st[1], dt, fa::kWideT))) return rc;
+      if ((rc = make_map(&pl.m.v64, key.ptr[2], B, H, Nkv, D, key.st[2], dt, fa::kWideT))) return rc;
+      if ((rc = make_map(&pl.m.do64, key.ptr[3], B, H, Nq, D, key.st[3], dt, fa::kWideT))) return rc;
+      if ((rc = make_map(&pl.m.dq16, key.ptr[7], B, H, Nq, D, key.st[6], dt, fa::kTileM))) return rc;
+    }
     if (plans.size() < kCap) {
       plans.push_back(pl);
     } else {
@@ -1214,10 +1276,12 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   canon_strides(dqs, B, H, Nq, D);
   canon_strides(dks, B, H, Nkv, D);
   canon_strides(dvs, B, H, Nkv, D);
-  const bool tc = (D % 8 == 0) && (D <= 128) && tma_ok_strides(p.qs) && tma_ok_strides(p.ks) &&
-                  tma_ok_strides(p.vs) && tma_ok_strides(dos) && tma_ok_strides(dks) &&
-                  tma_ok_strides(dvs) && aligned16(q) && aligned16(k) && aligned16(v) &&
-                  aligned16(d_o) && aligned16(dk) && aligned16(dv) && aligned16(dq_accum);
+  const bool tma_ok = (D % 8 == 0) && tma_ok_strides(p.qs) && tma_ok_strides(p.ks) && tma_ok_strides(p.vs) &&
+                      tma_ok_strides(dos) && tma_ok_strides(dks) && tma_ok_strides(dvs) && aligned16(q) &&
+                      aligned16(k) && aligned16(v) && aligned16(d_o) && aligned16(dk) && aligned16(dv);
+  const bool wide_tc = tma_ok && D > 128 && D <= 256 && tma_ok_strides(dqs) && aligned16(dq) &&
+                       g_bwd_kernel.load() != 3;  // fa_set_bwd_kernel(3) forces the CUDA-core kernels (tests)
+  const bool tc = (tma_ok && D <= 128 && aligned16(dq_accum)) || wide_tc;
   if (!tc && D > fa::kSimtMaxD) return fail(FA_ERR_UNSUPPORTED, "head dim > 1024 is not supported");
   int dev;
   if ((rc = check_device(&dev))) return rc;
@@ -1226,7 +1290,7 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   const int64_t rows = int64_t(B) * H * Nq;
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   // 1. delta = rowsum(dO o O), dq_accum = 0 (the generic path does not use the accumulator)
-  const int acc_ld = tc ? D : 0;
+  const int acc_ld = (tc && !wide_tc) ? D : 0;
   if (dtype == FA_DTYPE_BF16)
     fa::fa_bwd_delta_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta, dq_accum,
@@ -1272,7 +1336,7 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   // 2. main kernel
   BwdMaps m;
   BwdPlan key{};
-  const void* ptrs[7] = {q, k, v, d_o, dk, dv, dq_accum};
+  const void* ptrs[8] = {q, k, v, d_o, dk, dv, wide_tc ? nullptr : dq_accum, wide_tc ? dq : nullptr};
   memcpy(key.ptr, ptrs, sizeof ptrs);
   key.B = B; key.H = H; key.Nq = Nq; key.Nkv = Nkv; key.D = D; key.dtype = dtype; key.device = dev;
   memcpy(key.st[0], p.qs, sizeof p.qs);
@@ -1281,7 +1345,12 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   memcpy(key.st[3], dos, sizeof dos);
   memcpy(key.st[4], dks, sizeof dks);
   memcpy(key.st[5], dvs, sizeof dvs);
+  memcpy(key.st[6], dqs, sizeof dqs);
   if ((rc = g_bwd_plans.get(key, &m))) return rc;
+  if (wide_tc) {
+    fa::BwdWideParams wp{lse, delta, Nq, Nkv, H, scale * 1.4426950408889634f, 1.f};
+    return dispatch_bwd_wide(m, wp, B, H, Nq, Nkv, D, dtype, causal, scale, dev, st);
+  }
   fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale};
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 

@@ -34,7 +34,7 @@ __all__ = [
 
 _TMA_D_ALIGN = 8  # head dim multiple of 16 bytes for the tensor-core (TMA) kernels
 _TC_MAX_D = 256      # forward: ws / sk / tc1 kernels up to 128, the wide kernel up to 256
-_TC_MAX_D_BWD = 128  # tcgen05 backward kernel; larger head dims run the generic CUDA-core backward
+_TC_MAX_D_BWD = 256  # tcgen05 backward kernels (fa_bwd_ws up to 128, fa_bwd_wide up to 256); larger head dims run the generic CUDA-core backward
 
 
 def _raw_stream(dev_index: int) -> int:
@@ -141,7 +141,8 @@ def _backward(qp, kp, vp, o_full, d_o, lse, D, causal, scale, bnhd):
     """dQ, dK, dV on the tensors the forward saved (head dim padded to a multiple of 8).  Replaces
     backward_fp16 / backward_bf16 (kernel_fp16.cu:878-1028): the incoming gradient is zero-padded
     in the head dim like there (:903-917), the three gradients come back sliced to ``D``.  Head dims up to
-    128 run the tcgen05 kernel, larger ones (the reference pads and serves any, :900) the generic CUDA-core
+    128 run the pipelined tcgen05 kernel (csrc/fa_bwd_ws.cuh), 129..256 the three-launch tcgen05 kernel
+    (csrc/fa_bwd_wide.cuh), larger ones (the reference pads and serves any, :900) the generic CUDA-core
     backward (csrc/fa_bwd_simt.cuh)."""
     if not qp.is_cuda:
         raise RuntimeError("rocwmma_fattn (B200 build) runs on CUDA tensors only; there is no CPU fallback")
@@ -158,7 +159,8 @@ def _backward(qp, kp, vp, o_full, d_o, lse, D, causal, scale, bnhd):
     B, H, Nq, _ = _logical_shape(qp, bnhd)
     Nkv = _logical_shape(kp, bnhd)[2]
     dq, dk, dv = torch.empty_like(qp), torch.empty_like(kp), torch.empty_like(vp)
-    dq_acc = torch.empty((B, H, Nq, DP), dtype=torch.float32, device=qp.device)
+    # fp32 dQ accumulator of the head-dim <= 128 kernel (the other kernels write dQ directly: a token buffer)
+    dq_acc = torch.empty((B, H, Nq, DP) if DP <= 128 else (8,), dtype=torch.float32, device=qp.device)
     delta = torch.empty((B, H, Nq), dtype=torch.float32, device=qp.device)
     st = lambda t: _capi.strides4(_logical_strides(t, bnhd))  # noqa: E731
     with torch.cuda.device(qp.device):

@@ -196,14 +196,22 @@ def test_backward_baseline_shape_sampled_rows():
 
 
 WIDE_BWD_SHAPES = [
-    # B, H, Nq, Nkv, D: head dims above 128 (the reference pads and serves any, kernel_fp16.cu:900) run the
-    # generic CUDA-core backward (csrc/fa_bwd_simt.cuh)
+    # B, H, Nq, Nkv, D: head dims above 128 (the reference pads and serves any, kernel_fp16.cu:900).  129..256 run the
+    # three-launch tcgen05 kernel (csrc/fa_bwd_wide.cuh), larger ones the generic CUDA-core backward (csrc/fa_bwd_simt.cuh)
     (1, 2, 300, 300, 160),   # SD 1.5 head dim
     (2, 1, 257, 130, 192),
     (1, 2, 128, 384, 256),
+    (1, 2, 640, 640, 256),   # several streamed tiles per CTA: both stages of the ring wrap, single-stage modes too
+    (2, 3, 1000, 700, 160),  # unaligned, Nq != Nkv, more queries than keys
+    (1, 2, 130, 1000, 232),  # causal with keys beyond the last query: whole key tiles get zero gradients
     (1, 1, 200, 77, 264),    # above 256: generic forward AND backward
     (1, 2, 193, 150, 135),   # odd head dim, padded to 136
 ]
+
+
+def _is_wide_tc(D):
+    DP = -(-D // 8) * 8
+    return 128 < DP <= 256
 
 
 @pytest.mark.parametrize("causal", [False, True])
@@ -217,8 +225,30 @@ def test_backward_head_dims_above_128_match_fp32_autograd(shape, dtype, causal):
     ref, b16 = truth(q, k, v, d_o, causal)
     n0 = _capi.launch_count()
     _, dq, dk, dv = grads(q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV), causal)
-    assert _capi.launch_count() == n0 + 1 + 3  # forward; pre-pass, dQ kernel, dK/dV kernel
-    assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal} (generic backward)")
+    # forward; pre-pass + (dV, dK, dQ launches of the tcgen05 kernel | dQ kernel, dK/dV kernel of the generic path)
+    assert _capi.launch_count() == n0 + 1 + (4 if _is_wide_tc(D) else 3)
+    assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal}")
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_wide_backward_agrees_with_the_generic_cuda_core_backward(causal):
+    """fa_set_bwd_kernel(3) forces the CUDA-core kernels at head dims 129..256 too: two independent implementations
+    of the same gradients (fp32 math there, 16-bit P / dS on the tensor cores here)."""
+    B, H, Nq, Nkv, D = 1, 2, 384, 320, 192
+    q, k, v = orc.make_inputs(B, H, Nq, Nkv, D, F16, seed=11)
+    d_o = torch.rand((B, H, Nq, D), generator=torch.Generator().manual_seed(12)).to(F16)
+    args = (q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV))
+    tc = grads(*args, causal)[1:]
+    prev = _capi.set_bwd_kernel(3)
+    try:
+        n0 = _capi.launch_count()
+        simt = grads(*args, causal)[1:]
+        assert _capi.launch_count() == n0 + 1 + 3
+    finally:
+        _capi.set_bwd_kernel(prev)
+    for nm, a, b in zip(("dq", "dk", "dv"), tc, simt):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 4e-3 * max(1e-3, b.float().abs().max().item()) + 1e-5, f"{nm}: kernels disagree by {err:.3e}"
 
 
 def test_backward_of_unaligned_views_takes_the_tensor_core_kernel_on_contiguous_copies():
