@@ -742,6 +742,21 @@ def main():
             bwd["kernel"] = "fa_bwd_ws_kernel (pipelined, warp-specialised) + delta pre-pass + dQ conversion; 3 launches per call"
             extras[name_b] = bwd
 
+        # backward at the other head dims (SD 1.5 trains at 160): fa_bwd_ws at 64, the three-launch fa_bwd_wide above 128
+        bwd_hd = {}
+        for d_head in (64, 160, 256):
+            n = 4096
+            q, k, v, d_o = (torch.rand((1, H, n, d_head), dtype=dtype, device=dev) for _ in range(4))
+            _, qp, kp, vp, o_pad, lse = flash_attn_wmma.forward(q, k, v, 64, 128, False, d_head ** -0.5, False)
+
+            def bfn(*_a, n=n, qp=qp, kp=kp, vp=vp, o_pad=o_pad, d_o=d_o, lse=lse, dh=d_head):
+                return flash_attn_wmma.backward(qp, kp, vp, o_pad, d_o, lse, n, n, dh, 128, 128, False, dh ** -0.5, False)
+
+            fl = 2.5 * flops(1, H, n, d_head)
+            ms = time_variant(bfn, [(None, None, None)] * 2, False, fl)
+            bwd_hd[f"d{d_head}_n{n}"] = {"ms": round(ms, 5), "tflops": round(fl / (ms * 1e-3) / 1e12, 2)}
+        extras["f16_backward_head_dims"] = bwd_hd
+
         # the reference's head-dim sweep (bench_with_sdpa.py:259-283: D = 16 i at N = 4096) and the SD head dims at
         # N = 16384: ws3 at D <= 64, ws/sk up to 128, wide / wide2 (one Q tile per CTA, CTA pairs above 192) above
         hd = {}
