@@ -195,11 +195,13 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
         }
       }
       tc_commit(bar_mma1);
-      // two stages: the tile of iteration it+1 goes where iteration it-1's was, once its output product is done
-      if (kS == 2 && it >= 1 && it + 1 < n_iter) {
+      // two stages: the tile of iteration it+1 goes where iteration it-1's was, once its output product is done.
+      // (Phase it-1 is observed here in EVERY iteration, before phase it can complete: a parity wait cannot tell
+      // phase n from phase n+2 - compute-sanitizer's slow clock turned the missing wait into a deadlock.)
+      if (kS == 2 && it >= 1) {
         mbar_wait(bar_mma2, waited2 & 1, 82);
         ++waited2;
-        load_str(it + 1);
+        if (it + 1 < n_iter) load_str(it + 1);
       }
     }
 

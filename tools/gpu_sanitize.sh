@@ -8,7 +8,9 @@ import torch
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F
 torch.manual_seed(0)
 for (B, H, N, Nkv, D, dt, causal) in [(1, 2, 512, 512, 128, torch.float16, False), (1, 1, 300, 200, 128, torch.bfloat16, True),
-                                      (1, 2, 128, 128, 64, torch.float16, False), (1, 1, 384, 384, 64, torch.bfloat16, True)]:
+                                      (1, 2, 128, 128, 64, torch.float16, False), (1, 1, 384, 384, 64, torch.bfloat16, True),
+                                      # head dims 129..256: wide forward + the three-launch tcgen05 backward (fa_bwd_wide.cuh)
+                                      (1, 1, 320, 200, 160, torch.float16, True), (1, 2, 256, 384, 256, torch.bfloat16, False)]:
     q = torch.rand(B, H, N, D, dtype=dt, device="cuda", requires_grad=True)
     k = torch.rand(B, H, Nkv, D, dtype=dt, device="cuda", requires_grad=True)
     v = torch.rand(B, H, Nkv, D, dtype=dt, device="cuda", requires_grad=True)
