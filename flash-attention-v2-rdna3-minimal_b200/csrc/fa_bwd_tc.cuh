@@ -107,6 +107,71 @@ fa_bwd_dq_convert_kernel(const float* __restrict__ dq_acc, T* __restrict__ dq, i
   for (int d = lane; d < D; d += 32) dst[d] = static_cast<T>(src[d] * scale);
 }
 
+// The same two passes for 16-byte-aligned rows and head dims that are a multiple of 8 (everything the tensor-core
+// kernels take): 16-byte loads and stores, 16 lanes per row (two rows per warp) up to head dim 128.  At N <= 4096 the
+// passes are 10-30 % of a backward call, so their bandwidth matters: the scalar versions above move 2 bytes per lane
+// and instruction.
+template <typename T, int kLanes>
+__global__ void __launch_bounds__(256)
+fa_bwd_delta_vec_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta,
+                        float* __restrict__ dq_acc, int B, int H, int Nq, int D, int dq_ld, int64_t os0,
+                        int64_t os1, int64_t os2, int64_t ds0, int64_t ds1, int64_t ds2) {
+  constexpr int kRowsPerWarp = 32 / kLanes;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % kLanes;
+  const int64_t row_id = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kRowsPerWarp + lane / kLanes;
+  const int64_t total = static_cast<int64_t>(B) * H * Nq;
+  const bool live = row_id < total;
+  float acc = 0.f;
+  if (live) {
+    const int n = static_cast<int>(row_id % Nq);
+    const int h = static_cast<int>((row_id / Nq) % H);
+    const int b = static_cast<int>(row_id / (static_cast<int64_t>(Nq) * H));
+    const uint4* po = reinterpret_cast<const uint4*>(o + b * os0 + h * os1 + n * os2);
+    const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * ds0 + h * ds1 + n * ds2);
+    for (int c = sub; c < D / 8; c += kLanes) {
+      const uint4 a = __ldg(po + c), g = __ldg(pd + c);
+      const T* av = reinterpret_cast<const T*>(&a);
+      const T* gv = reinterpret_cast<const T*>(&g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(static_cast<float>(av[e]), static_cast<float>(gv[e]), acc);
+    }
+    float4* pq = reinterpret_cast<float4*>(dq_acc + row_id * dq_ld);
+    for (int c = sub; c < dq_ld / 4; c += kLanes) pq[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int off = kLanes / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (live && sub == 0) delta[row_id] = acc;
+}
+
+template <typename T, int kLanes>
+__global__ void __launch_bounds__(256)
+fa_bwd_dq_convert_vec_kernel(const float* __restrict__ dq_acc, T* __restrict__ dq, int B, int H, int Nq, int D,
+                             int dq_ld, int64_t s0, int64_t s1, int64_t s2, float scale) {
+  pdl_wait();  // launched with programmatic stream serialization behind the main kernel
+  constexpr int kRowsPerWarp = 32 / kLanes;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % kLanes;
+  const int64_t row_id = (static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kRowsPerWarp + lane / kLanes;
+  const int64_t total = static_cast<int64_t>(B) * H * Nq;
+  if (row_id >= total) return;
+  const int n = static_cast<int>(row_id % Nq);
+  const int h = static_cast<int>((row_id / Nq) % H);
+  const int b = static_cast<int>(row_id / (static_cast<int64_t>(Nq) * H));
+  const float4* src = reinterpret_cast<const float4*>(dq_acc + row_id * dq_ld);
+  uint4* dst = reinterpret_cast<uint4*>(dq + b * s0 + h * s1 + n * s2);
+  for (int c = sub; c < D / 8; c += kLanes) {
+    const float4 lo = src[2 * c], hi = src[2 * c + 1];
+    uint4 out;
+    T* ov = reinterpret_cast<T*>(&out);
+    ov[0] = static_cast<T>(lo.x * scale); ov[1] = static_cast<T>(lo.y * scale);
+    ov[2] = static_cast<T>(lo.z * scale); ov[3] = static_cast<T>(lo.w * scale);
+    ov[4] = static_cast<T>(hi.x * scale); ov[5] = static_cast<T>(hi.y * scale);
+    ov[6] = static_cast<T>(hi.z * scale); ov[7] = static_cast<T>(hi.w * scale);
+    dst[c] = out;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // main kernel: one CTA per (batch, head, 128-key tile)
 // ---------------------------------------------------------------------------------------------

@@ -1291,14 +1291,31 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   // 1. delta = rowsum(dO o O), dq_accum = 0 (the generic path does not use the accumulator)
   const int acc_ld = (tc && !wide_tc) ? D : 0;
-  if (dtype == FA_DTYPE_BF16)
+  // 16-byte vector version when every row of O and dO (and of the accumulator) can be read that way
+  const bool vec_rows = (D % 8 == 0) && aligned16(o) && aligned16(d_o) && aligned16(dq_accum) && tma_ok_strides(p.os) &&
+                        tma_ok_strides(dos) && (acc_ld % 4 == 0);
+  if (vec_rows) {
+    const bool narrow = D <= 128;  // 16 lanes per row, two rows per warp
+    const unsigned vblocks = static_cast<unsigned>((rows + (narrow ? 15 : 7)) / (narrow ? 16 : 8));
+#define FA_DELTA_VEC(T, LANES)                                                                                  \
+  fa::fa_bwd_delta_vec_kernel<T, LANES><<<vblocks, 256, 0, st>>>(static_cast<const T*>(o), static_cast<const T*>(d_o), \
+                                                                 delta, dq_accum, B, H, Nq, D, acc_ld, p.os[0], \
+                                                                 p.os[1], p.os[2], dos[0], dos[1], dos[2])
+    if (dtype == FA_DTYPE_BF16) {
+      if (narrow) FA_DELTA_VEC(__nv_bfloat16, 16); else FA_DELTA_VEC(__nv_bfloat16, 32);
+    } else {
+      if (narrow) FA_DELTA_VEC(__half, 16); else FA_DELTA_VEC(__half, 32);
+    }
+#undef FA_DELTA_VEC
+  } else if (dtype == FA_DTYPE_BF16) {
     fa::fa_bwd_delta_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta, dq_accum,
         B, H, Nq, D, acc_ld, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
-  else
+  } else {
     fa::fa_bwd_delta_kernel<__half><<<blocks, 256, 0, st>>>(
         static_cast<const __half*>(o), static_cast<const __half*>(d_o), delta, dq_accum, B, H, Nq, D,
         acc_ld, p.os[0], p.os[1], p.os[2], dos[0], dos[1], dos[2]);
+  }
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 
@@ -1355,12 +1372,21 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 
   // 3. dQ = scale * dq_accum
-  if (dtype == FA_DTYPE_BF16)
+  if ((D % 8 == 0) && aligned16(dq) && tma_ok_strides(dqs)) {
+    const unsigned vblocks = static_cast<unsigned>((rows + 15) / 16);  // D <= 128 here: 16 lanes per row
+    if (dtype == FA_DTYPE_BF16)
+      fa::fa_bwd_dq_convert_vec_kernel<__nv_bfloat16, 16><<<vblocks, 256, 0, st>>>(
+          dq_accum, static_cast<__nv_bfloat16*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
+    else
+      fa::fa_bwd_dq_convert_vec_kernel<__half, 16><<<vblocks, 256, 0, st>>>(
+          dq_accum, static_cast<__half*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
+  } else if (dtype == FA_DTYPE_BF16) {
     fa::fa_bwd_dq_convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         dq_accum, static_cast<__nv_bfloat16*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
-  else
+  } else {
     fa::fa_bwd_dq_convert_kernel<__half><<<blocks, 256, 0, st>>>(
         dq_accum, static_cast<__half*>(dq), B, H, Nq, D, D, dqs[0], dqs[1], dqs[2], scale);
+  }
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
