@@ -42,6 +42,7 @@ struct BwdParams {
   int dq_ld;           // row pitch of dq_acc in floats (the padded head dim)
   float scale_log2;    // scale * log2(e)
   float scale;
+  int lpt_group;       // fa_bwd_ws.cuh, causal: (batch, head) pairs per longest-first group of the 1-D grid
 };
 
 template <int kDP>

@@ -90,17 +90,21 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  // Causal launches are a 1-D grid ordered LONGEST KEY TILE FIRST ACROSS HEADS (key tile j walks the query tiles
-  // j..end, so its work falls with j; with the (j, h, b) grid every head's long tiles queued behind the short tiles
-  // of the heads before it and the launch ended on a few long stragglers - the forward's work_coords, mirrored).
-  // (launch_bwd_ws uses it up to ten rounds of CTAs; beyond that the tail is short and keeping a head's key tiles
-  // together is worth more in L2: N=16384 H=16 1043 vs 1033 TFLOPS.)
+  // Causal launches are a 1-D grid ordered LONGEST KEY TILE FIRST ACROSS A GROUP OF HEADS (key tile j walks the query
+  // tiles j..end, so its work falls with j; with the (j, h, b) grid every head's long tiles queued behind the short
+  // tiles of the heads before it and the launch ended on a few long stragglers - the forward's work_coords, mirrored).
+  // A group is p.lpt_group (batch, head) pairs - about four rounds of CTAs, so that the Q / dO tiles the group streams
+  // stay in L2; small problems are one group.
   int j, h, b;
   if (kCausal && gridDim.y == 1 && gridDim.z == 1) {
     const int n_j = (p.Nkv + kTileN - 1) / kTileN;
     const int hb_count = static_cast<int>(gridDim.x) / n_j;
-    j = static_cast<int>(blockIdx.x) / hb_count;
-    const int hb = static_cast<int>(blockIdx.x) % hb_count;
+    const int per_group = p.lpt_group * n_j;
+    const int g = static_cast<int>(blockIdx.x) / per_group;
+    const int rem = static_cast<int>(blockIdx.x) - g * per_group;
+    const int members = min(p.lpt_group, hb_count - g * p.lpt_group);  // the last group may be smaller
+    j = rem / members;
+    const int hb = g * p.lpt_group + rem % members;
     h = hb % p.H;
     b = hb / p.H;
   } else {

@@ -695,16 +695,20 @@ template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_ws(const BwdMaps& m, const fa::BwdParams& bp, int B, int H, int Nkv, int device,
                   cudaStream_t stream) {
   const unsigned n_j = static_cast<unsigned>((Nkv + fa::kTileN - 1) / fa::kTileN);
-  // causal: longest key tile first across heads (1-D grid, see the kernel) while the launch is at most ten rounds
+  // causal: 1-D grid, longest key tile first across groups of (batch, head) pairs of about four rounds of CTAs (see the kernel)
   const unsigned ctas = n_j * static_cast<unsigned>(H) * static_cast<unsigned>(B);
+  // ... up to ten rounds of CTAs: beyond that (N=16384, H=16: 13.8 rounds) the natural order - a head's key tiles next to each
+  // other, walking the same query tiles almost in step - measures better (1075 vs 1045 TFLOPS) than any longest-first order
   const dim3 grid = (kCausal && ctas <= 10u * 148u) ? dim3(ctas, 1, 1)
                                                     : dim3(n_j, static_cast<unsigned>(H), static_cast<unsigned>(B));
+  fa::BwdParams bpl = bp;
+  bpl.lpt_group = std::max(1, std::min(H * B, static_cast<int>((4u * 148u + n_j / 2) / n_j)));
   auto kernel = fa::fa_bwd_ws_kernel<kDP, kBF16, kCausal>;
   constexpr int smem = fa::BwdWsSmem<kDP>::kTotal;
   static std::atomic<uint64_t> configured{0};
   int rc = set_smem(kernel, smem, &configured, device);
   if (rc) return rc;
-  kernel<<<grid, fa::kBwdWsThreads, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq32, bp);
+  kernel<<<grid, fa::kBwdWsThreads, smem, stream>>>(m.q, m.k, m.v, m.d_o, m.dk, m.dv, m.dq32, bpl);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
@@ -1368,7 +1372,7 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
     fa::BwdWideParams wp{lse, delta, Nq, Nkv, H, scale * 1.4426950408889634f, 1.f};
     return dispatch_bwd_wide(m, wp, B, H, Nq, Nkv, D, dtype, causal, scale, dev, st);
   }
-  fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale};
+  fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale, 1};
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 
   // 3. dQ = scale * dq_accum

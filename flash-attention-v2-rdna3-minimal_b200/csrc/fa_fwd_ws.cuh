@@ -163,6 +163,12 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   // keeps m_run anyway (max grew by < 2^8); otherwise the slow path below redoes the columns.
   float nmc = -m_run * c;
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#if FA_PAIR_SYNC_MODE == 3
+  // experiment: the same loop inside a one-trip loop whose bound the compiler cannot see (Nkv > 0), i.e. a basic
+  // block of its own: ptxas cannot sink its MUFU instructions behind the BAR.SYNC below
+#pragma unroll 1
+  for (int rep = 0; rep < (Nkv > 0 ? 1 : 0); ++rep) {
+#endif
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
@@ -171,6 +177,9 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
     exp4(i, nmc);
   }
+#if FA_PAIR_SYNC_MODE == 3
+  }
+#endif
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   FA_TRS(0);
   *my_max = mx;
