@@ -181,11 +181,12 @@ def set_kernel(kernel: int) -> int:
     return prev
 
 
-FA_BWD_KERNEL_AUTO, FA_BWD_KERNEL_TC, FA_BWD_KERNEL_WS = 0, 1, 2
+FA_BWD_KERNEL_AUTO, FA_BWD_KERNEL_TC, FA_BWD_KERNEL_WS, FA_BWD_KERNEL_SIMT_ABOVE_128 = 0, 1, 2, 3
 
 
 def set_bwd_kernel(kernel: int) -> int:
-    """Backward kernel for head dims <= 128 (test hook): 0 auto, 1 serial (fa_bwd_tc), 2 pipelined (fa_bwd_ws)."""
+    """Backward kernel (test hook): 0 auto, 1 serial (fa_bwd_tc), 2 pipelined (fa_bwd_ws) at head dims <= 128; 3 forces
+    the CUDA-core kernels at head dims 129..256 (default there: the three-launch tcgen05 kernel fa_bwd_wide)."""
     return int(lib.fa_set_bwd_kernel(int(kernel)))
 
 

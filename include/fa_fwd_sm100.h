@@ -119,16 +119,17 @@ int fa_host_sync(void);
  *   d_o          gradient of the loss w.r.t. o, [B,H,Nq,D] logical, strides do_strides
  *   lse          the forward's base-2 log-sum-exp, contiguous fp32 [B,H,Nq] (fa_fwd_sm100 `lse`)
  *   dq, dk, dv   outputs, shaped / typed like q, k, v; strides dq_strides / dk_strides / dv_strides
- *   dq_accum     caller-owned fp32 workspace, contiguous [B,H,Nq,D] (zeroed here); dQ is accumulated
- *                across key tiles with fp32 atomics - the reference adds into a 16-bit dQ from
- *                several CTAs without atomics (kernel_fp16.cu:736)
+ *   dq_accum     caller-owned fp32 workspace: contiguous [B,H,Nq,D] for D <= 128 (zeroed here; dQ is accumulated across key
+ *                tiles with fp32 reduce-adds - the reference adds into a 16-bit dQ from several CTAs without atomics,
+ *                kernel_fp16.cu:736), any non-null 16-byte-aligned buffer of at least 8 floats otherwise (unused)
  *   delta        caller-owned fp32 workspace, contiguous [B,H,Nq]; receives rowsum(dO o O)
  *                (what the reference recomputes in every CTA, kernel_fp16.cu:605-631)
  *
- * Tensor-core path only: D % 8 == 0, D <= 128, 16-byte aligned pointers and strides, innermost
- * strides 1; anything else returns FA_ERR_UNSUPPORTED (the Python layer pads the head dim exactly
- * as the reference's launcher does, kernel_fp16.cu:903-917).  Three launches (pre-pass, main kernel,
- * dQ conversion) on `stream`, asynchronous with respect to the host.
+ * Kernels: D % 8 == 0 with 16-byte aligned pointers and strides runs on the tensor cores - D <= 128: pre-pass, the pipelined
+ * kernel fa_bwd_ws.cuh, dQ conversion (3 launches); 128 < D <= 256: pre-pass + one launch each for dV, dK and dQ of
+ * fa_bwd_wide.cuh (4 launches, dQ written directly).  Everything else the forward accepts (D up to 1024, any alignment) runs
+ * the generic CUDA-core kernels (pre-pass + 2 launches).  D > 1024 returns FA_ERR_UNSUPPORTED.  Innermost strides must be 1.
+ * All launches go to `stream`, asynchronous with respect to the host.
  */
 int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                  const float* lse, void* dq, void* dk, void* dv, float* dq_accum, float* delta, int B,

@@ -29,8 +29,10 @@ int fa_set_pdl(int enable);
  * heuristic.  Test / benchmarking hook.  Returns the previous setting. */
 int fa_set_kernel(int kernel);
 
-/* Backward kernel for head dims <= 128: 0 = automatic (the pipelined, warp-specialised kernel fa_bwd_ws.cuh),
- * 1 = the serial kernel fa_bwd_tc.cuh (round 1), 2 = fa_bwd_ws.cuh.  Returns the previous setting. */
+/* Backward kernel selection (test / benchmarking hook).  Head dims <= 128: 0 = automatic (the pipelined, warp-specialised
+ * kernel fa_bwd_ws.cuh), 1 = the serial kernel fa_bwd_tc.cuh (round 1), 2 = fa_bwd_ws.cuh.  Head dims 129..256 run the
+ * three-launch tcgen05 kernel fa_bwd_wide.cuh unless 3 is set, which forces the generic CUDA-core kernels (fa_bwd_simt.cuh)
+ * there as well.  Returns the previous setting. */
 int fa_set_bwd_kernel(int kernel);
 
 /*

@@ -239,7 +239,7 @@ def test_wide_backward_agrees_with_the_generic_cuda_core_backward(causal):
     d_o = torch.rand((B, H, Nq, D), generator=torch.Generator().manual_seed(12)).to(F16)
     args = (q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV))
     tc = grads(*args, causal)[1:]
-    prev = _capi.set_bwd_kernel(3)
+    prev = _capi.set_bwd_kernel(_capi.FA_BWD_KERNEL_SIMT_ABOVE_128)
     try:
         n0 = _capi.launch_count()
         simt = grads(*args, causal)[1:]
