@@ -44,7 +44,7 @@ struct WsCfg {
   static constexpr int kQ = 0;                           // 2 Q tiles (re-used as O staging)
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kBars = kKV + kStages * kTileBytes;
-  static constexpr int kNumBars = 22 + 2 * kStages;  // 14 pipeline + 8 row-pair exchange + the K/V ring
+  static constexpr int kNumBars = 14 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;      // float [2 parity][2 tile][2 half][128]
   static constexpr int kFinal = kMax + 2 * 2 * 2 * 128 * 4;   // float [2 tile][2 half][128] row sums
   static constexpr int kTotal = kFinal + 2 * 2 * 128 * 4 + 1024;  // + alignment slack
@@ -57,6 +57,8 @@ struct WsCfg {
   do {                                                                                      \
     if (tr_on && lane == 0) p.trace[((role) * 128 + ((j) & 127)) * 8 + (ev)] = clock64();   \
   } while (0)
+// (the same inside ws_softmax_step: stamps of the step's phases, tools/trace_ws_softmax.py; note that the stamps change
+// what ptxas does with the step - the traced kernel issues its first-half exponentials before the pair barrier)
 #define FA_TRS_PARAM , unsigned long long* trp = nullptr
 #define FA_TRS(ev) do { if (trp != nullptr && lane == 0) trp[ev] = clock64(); } while (0)
 #else
@@ -72,23 +74,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: rescale O only when th
 #define FA_EMU_PAIRS 1
 #endif
 constexpr int kEmuPairs = FA_EMU_PAIRS;
-// separate shares for columns [0,32) / [32,64) of a thread (experiment: the tile that has just started its step
-// leaves the MUFU to the tile that is finishing); default: the same share everywhere
-#ifndef FA_EMU_PAIRS_FIRST
-#define FA_EMU_PAIRS_FIRST FA_EMU_PAIRS
-#endif
-#ifndef FA_EMU_PAIRS_SECOND
-#define FA_EMU_PAIRS_SECOND FA_EMU_PAIRS
-#endif
 // Turn-taking between the softmax groups of the two Q tiles (experiment): tile 1 starts its step on KV
 // tile j only after tile 0 has issued its last exponentials of step j, and tile 0 starts step j+1
 // only after tile 1's step j, so the two groups never compete for the MUFU.
-#ifndef FA_PART_ORDER
-#define FA_PART_ORDER 1
-#endif
-#ifndef FA_PAIR_SYNC_MODE
-#define FA_PAIR_SYNC_MODE 0
-#endif
 #ifndef FA_SEQ
 #define FA_SEQ 0
 #endif
@@ -113,15 +101,14 @@ constexpr int kPvParts = FA_PV_PARTS;
 //   have_o      O_t already holds a partial sum (not the first KV tile of this pass)
 //   bar_o       0, or the mbarrier (with parity o_parity) that tells PV(j-1) has left the tensor cores
 //   kPairArrive the P barriers are shared::cluster addresses in the leader CTA of a CTA pair (wide2 kernel)
-template <int kDP, bool kBF16, bool kPairArrive = false, bool kPairMbar = false>
+template <int kDP, bool kBF16, bool kPairArrive = false>
 __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
                                                 float* my_max, const float* other_max, int pair_bar,
                                                 uint32_t bar_early, uint32_t bar_late,
                                                 uint32_t bar_turn = 0u, uint32_t bar_mid = 0u,
-                                                uint32_t bar_o = 0u, uint32_t o_parity = 0u,
-                                                uint32_t pair_mbar = 0u, uint32_t pair_parity = 0u FA_TRS_PARAM) {
+                                                uint32_t bar_o = 0u, uint32_t o_parity = 0u FA_TRS_PARAM) {
   constexpr int kOHalf = kDP / 2;
   const bool tail = (col0 + 64 > Nkv);
   const bool masked = tail || diag;
@@ -142,18 +129,17 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   auto exp4 = [&](int i, float nmc_) {
     ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc_, nmc_);
     ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc_, nmc_);
-    const int ke = (i < 32) ? FA_EMU_PAIRS_FIRST : FA_EMU_PAIRS_SECOND;
-    if ((((i >> 1) * ke) & 7) < ke) {
+    if ((((i >> 1) * kEmuPairs) & 7) < kEmuPairs) {
       ex2_fma2(s[i], s[i + 1]);
     } else {
-      s[i] = ex2_approx_pinned(s[i]);
-      s[i + 1] = ex2_approx_pinned(s[i + 1]);
+      s[i] = ex2_approx(s[i]);
+      s[i + 1] = ex2_approx(s[i + 1]);
     }
-    if (((((i >> 1) + 1) * ke) & 7) < ke) {
+    if (((((i >> 1) + 1) * kEmuPairs) & 7) < kEmuPairs) {
       ex2_fma2(s[i + 2], s[i + 3]);
     } else {
-      s[i + 2] = ex2_approx_pinned(s[i + 2]);
-      s[i + 3] = ex2_approx_pinned(s[i + 3]);
+      s[i + 2] = ex2_approx(s[i + 2]);
+      s[i + 3] = ex2_approx(s[i + 3]);
     }
   };
 
@@ -163,12 +149,6 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   // keeps m_run anyway (max grew by < 2^8); otherwise the slow path below redoes the columns.
   float nmc = -m_run * c;
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#if FA_PAIR_SYNC_MODE == 3
-  // experiment: the same loop inside a one-trip loop whose bound the compiler cannot see (Nkv > 0), i.e. a basic
-  // block of its own: ptxas cannot sink its MUFU instructions behind the BAR.SYNC below
-#pragma unroll 1
-  for (int rep = 0; rep < (Nkv > 0 ? 1 : 0); ++rep) {
-#endif
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
@@ -177,22 +157,12 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
     exp4(i, nmc);
   }
-#if FA_PAIR_SYNC_MODE == 3
-  }
-#endif
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   FA_TRS(0);
+  // (ptxas schedules the MUFU instructions of the loop above BEHIND this barrier - SASS-checked in round 2 - so the
+  // chain is max -> exchange -> exponentials; forcing them in front of it measured 4.5-8 % slower)
   *my_max = mx;
-  if constexpr (kPairMbar) {
-    // Exchange through an mbarrier (2 arrivals per phase) instead of a named barrier: ptxas schedules the MUFU
-    // instructions of the loop above BEHIND a BAR.SYNC in the same basic block (SASS-checked, round 2), which put
-    // max -> barrier -> exponentials in series.  The polling loop is a block boundary it does not move them across.
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pair_mbar);
-    mbar_wait(pair_mbar, pair_parity, 45);
-  } else {
-    named_bar_sync(pair_bar, 64);
-  }
+  named_bar_sync(pair_bar, 64);
   FA_TRS(1);
   const float m_cand = fmaxf(fmaxf(mx, *other_max), m_run);
   // both threads of the row see the same three numbers, so they take the same decision
@@ -295,105 +265,6 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 }
 
-// The same step with the P hand-off in FOUR parts of 16 keys per half (k-steps {0,4} {1,5} {2,6} {3,7}) and every
-// exponential taken against the final running max: max -> pair exchange -> (rare) O rescale -> 4 x (16 exponentials,
-// pack, tcgen05.st, arrive).  Written in the order ptxas schedules the 3-part step anyway (it sinks that step's
-// "speculative" exponentials behind the pair barrier, SASS-checked in round 2), so there is no redo path.  The two-tile
-// kernel is bound by the time to the FIRST hand-off (the tensor cores idle until then), which this halves.
-template <int kDP, bool kBF16>
-__device__ __forceinline__ void ws_softmax_step4(float (&s)[64], uint32_t tS, uint32_t tO, int half, int r, int lane,
-                                                 int col0, int Nkv, bool diag, float c, float& m_run, float& l_run,
-                                                 bool have_o, float* my_max, const float* other_max, int pair_bar,
-                                                 const uint32_t (&bar_part)[4], uint32_t zero_addr) {
-  constexpr int kOHalf = kDP / 2;
-  const bool tail = (col0 + 64 > Nkv);
-  if (tail || diag) {
-    const int valid = tail ? (Nkv - col0) : 64;
-    const int lim = diag ? min(valid, r + 1 - half * 64) : valid;
-#pragma unroll
-    for (int i = 0; i < 64; ++i)
-      if (i >= lim) s[i] = -INFINITY;
-  }
-  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 32]));
-    mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
-    mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
-    mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
-  }
-  const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-  *my_max = mx;
-  named_bar_sync(pair_bar, 64);
-  const float m_cand = fmaxf(fmaxf(mx, *other_max), m_run);
-  const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
-  float alpha = 1.f;
-  if (__any_sync(0xffffffffu, grow)) {
-    if (grow) {
-      alpha = ex2_approx((m_run - m_cand) * c);
-      m_run = m_cand;
-    }
-    if (have_o) {  // PV_t(j-1) has completed: it was issued before S_t(j), whose commit we waited for
-#pragma unroll 1
-      for (int c8 = 0; c8 < kOHalf; c8 += 8) {
-        uint32_t o[8];
-        tmem_ld_x8(tO + c8, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_x8(tO + c8, o);
-      }
-    }
-  }
-  float nmc = -m_run * c;
-  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-  for (int part = 0; part < 4; ++part) {
-    uint32_t pk[8];
-#pragma unroll
-    for (int i = 16 * part; i < 16 * part + 16; i += 4) {
-      ffma2(s[i], s[i + 1], s[i], s[i + 1], c, c, nmc, nmc);
-      ffma2(s[i + 2], s[i + 3], s[i + 2], s[i + 3], c, c, nmc, nmc);
-      constexpr int ke = FA_EMU_PAIRS;
-      if ((((i >> 1) * ke) & 7) < ke) {
-        ex2_fma2(s[i], s[i + 1]);
-      } else {
-        s[i] = ex2_approx_pinned(s[i]);
-        s[i + 1] = ex2_approx_pinned(s[i + 1]);
-      }
-      if (((((i >> 1) + 1) * ke) & 7) < ke) {
-        ex2_fma2(s[i + 2], s[i + 3]);
-      } else {
-        s[i + 2] = ex2_approx_pinned(s[i + 2]);
-        s[i + 3] = ex2_approx_pinned(s[i + 3]);
-      }
-      if (part > 0) {  // row sum of the previous part in the MUFU shadow
-        fadd2(sum0, sum1, sum0, sum1, s[i - 16], s[i - 15]);
-        fadd2(sum2, sum3, sum2, sum3, s[i - 14], s[i - 13]);
-      }
-      pk[(i - 16 * part) >> 1] = pack2<kBF16>(s[i], s[i + 1]);
-      pk[((i - 16 * part) >> 1) + 1] = pack2<kBF16>(s[i + 2], s[i + 3]);
-    }
-    tmem_st_x8(tS + 8 * part, pk);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_part[part]);
-#if FA_PART_ORDER
-    // ptxas otherwise hoists the exponentials of the later parts above this part's tcgen05.st (in-order issue: the
-    // hand-off then queues behind up to 40 MUFU instructions).  A 0.0f it cannot see through, loaded from shared
-    // memory AFTER the arrive, makes the next part's scores depend on the hand-off having been issued.
-    if (part < 3) nmc += ld_shared_volatile_f32(zero_addr);
-#endif
-  }
-#pragma unroll
-  for (int i = 48; i < 64; i += 4) {
-    fadd2(sum0, sum1, sum0, sum1, s[i], s[i + 1]);
-    fadd2(sum2, sum3, sum2, sum3, s[i + 2], s[i + 3]);
-  }
-  l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
-}
-
 // Epilogue building block shared by every two-threads-per-row kernel: my half of the normalised output row,
 // O / l, from tensor memory -> 16 bit -> the 128-byte-swizzled staging tile a TMA store reads.
 template <int kOHalf, bool kBF16, bool kUnroll = true>
@@ -455,10 +326,8 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_o_final = [&](int t) { return smem_u32(&bars[8 + t]); };     // tcgen05.commit
   auto bar_turn = [&](int t) { return smem_u32(&bars[10 + t]); };       // kSeq: 8 warps of the other tile
   auto bar_p_mid = [&](int t) { return smem_u32(&bars[12 + t]); };      // kPvParts == 3: 8 warps
-  auto bar_pair = [&](int i) { return smem_u32(&bars[14 + i]); };       // the two warps sharing 32 rows of a tile
-  auto bar_p_mid1 = [&](int t) { return smem_u32(&bars[16 + t]); };     // kPvParts == 4 (bar_pair 2, 3 are unused then)
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[22 + s]); };    // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[22 + kS + s]); };  // tcgen05.commit
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[14 + s]); };    // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[14 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -495,8 +364,6 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_p_mid(t), 8);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mbar_init(bar_pair(i), (kPvParts == 4 && (i == 2 || i == 3)) ? 8 : 2);
-#pragma unroll
     for (int s = 0; s < kS; ++s) {
       mbar_init(bar_kv_full(s), 1);
       mbar_init(bar_kv_empty(s), 1);
@@ -524,7 +391,6 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
     }
   }
-  if (warp == 17 && lane == 0) tmem_slot[1] = 0u;  // the 0.0f of ws_softmax_step4
   if (warp == 16) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
@@ -624,14 +490,12 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           mbar_wait(bar_p_early(t), j & 1, 31 + t);
           tc_fence_after();
           FA_TR(2, j, 2 + 3 * t);
-          if (kPvParts == 4) {  // parts of 16 keys per half: k-steps {0,4} {1,5} {2,6} {3,7}
-            pv_step(t, v_lo, 0, j > 0);
-            pv_step(t, v_lo, 4, 1);
+          pv_step(t, v_lo, 0, j > 0);
+          pv_step(t, v_lo, 1, 1);
+          pv_step(t, v_lo, 4, 1);
+          pv_step(t, v_lo, 5, 1);
+          if (kPvParts == 3) {
             mbar_wait(bar_p_mid(t), j & 1, 37 + t);
-            tc_fence_after();
-            pv_step(t, v_lo, 1, 1);
-            pv_step(t, v_lo, 5, 1);
-            mbar_wait(bar_p_mid1(t), j & 1, 39 + t);
             tc_fence_after();
             pv_step(t, v_lo, 2, 1);
             pv_step(t, v_lo, 6, 1);
@@ -640,27 +504,12 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
             pv_step(t, v_lo, 3, 1);
             pv_step(t, v_lo, 7, 1);
           } else {
-            pv_step(t, v_lo, 0, j > 0);
-            pv_step(t, v_lo, 1, 1);
-            pv_step(t, v_lo, 4, 1);
-            pv_step(t, v_lo, 5, 1);
-            if (kPvParts == 3) {
-              mbar_wait(bar_p_mid(t), j & 1, 37 + t);
-              tc_fence_after();
-              pv_step(t, v_lo, 2, 1);
-              pv_step(t, v_lo, 6, 1);
-              mbar_wait(bar_p_late(t), j & 1, 35 + t);
-              tc_fence_after();
-              pv_step(t, v_lo, 3, 1);
-              pv_step(t, v_lo, 7, 1);
-            } else {
-              mbar_wait(bar_p_late(t), j & 1, 35 + t);
-              tc_fence_after();
-              pv_step(t, v_lo, 2, 1);
-              pv_step(t, v_lo, 3, 1);
-              pv_step(t, v_lo, 6, 1);
-              pv_step(t, v_lo, 7, 1);
-            }
+            mbar_wait(bar_p_late(t), j & 1, 35 + t);
+            tc_fence_after();
+            pv_step(t, v_lo, 2, 1);
+            pv_step(t, v_lo, 3, 1);
+            pv_step(t, v_lo, 6, 1);
+            pv_step(t, v_lo, 7, 1);
           }
           if (j == n_t[t] - 1) tc_commit(bar_o_final(t));
         };
@@ -744,23 +593,15 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       FA_TR(tr_role, j, 2);
 
-      if constexpr (kPvParts == 4) {
-        const uint32_t bar_part[4] = {bar_p_early(t), bar_p_mid(t), bar_p_mid1(t), bar_p_late(t)};
-        ws_softmax_step4<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv, kCausal && (j == diag_j), c,
-                                     m_run, l_run, j > 0, my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
-                                     bar_part, smem_u32(tmem_slot + 1));
-      } else {
-        ws_softmax_step<kDP, kBF16, false, FA_PAIR_SYNC_MODE == 2>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
-                                    kCausal && (j == diag_j), c, m_run, l_run, j > 0,
-                                    my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
-                                    bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
-                                    bar_p_mid(t), 0u, 0u,
-                                    bar_pair(t * 4 + (warp & 3)), j & 1
-  #ifdef FA_TRACE
-                                    , (tr_on && j < 128) ? p.trace + ((5 + t) * 128 + j) * 8 : nullptr
-  #endif
-                                    );
-    }
+      ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
+                                  kCausal && (j == diag_j), c, m_run, l_run, j > 0,
+                                  my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
+                                  bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
+                                  bar_p_mid(t)
+#ifdef FA_TRACE
+                                  , 0u, 0u, (tr_on && j < 128) ? p.trace + ((5 + t) * 128 + j) * 8 : nullptr
+#endif
+                                  );
       FA_TR(tr_role, j, 6);
     }
 

@@ -54,27 +54,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// The same instruction as a volatile asm: it keeps its place relative to the other volatile asms (named barriers,
-// tcgen05.st, mbarrier arrives).  The softmax step uses it for the exponentials that must be ISSUED before the pair
-// barrier - the compiler otherwise sinks them to their first use, behind the barrier (SASS-checked, round 2).
-#ifndef FA_EX2_PINNED
-#define FA_EX2_PINNED 0
-#endif
-__device__ __forceinline__ float ex2_approx_pinned(float x) {
-  float y;
-#if FA_EX2_PINNED
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-#else
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-#endif
-  return y;
-}
-
-__device__ __forceinline__ float ld_shared_volatile_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization
