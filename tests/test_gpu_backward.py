@@ -230,6 +230,21 @@ def test_backward_head_dims_above_128_match_fp32_autograd(shape, dtype, causal):
     assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal}")
 
 
+def test_wide_backward_bnhd_layout_and_packed_qkv_views():
+    """[B,N,H,D] tensors that are views into one packed [B,N,3,H,D] buffer: the 64-row and 128-row tensor maps of the
+    head-dim 129..256 backward take the strides as they are (no copies), gradients come back in the same layout."""
+    B, H, N, D = 2, 3, 320, 160
+    qkv = torch.rand((B, N, 3, H, D), generator=torch.Generator().manual_seed(21)).to(F16).to(DEV)
+    q, k, v = (qkv[:, :, i] for i in range(3))  # BNHD views, row stride 3*H*D
+    d_o = torch.rand((B, N, H, D), generator=torch.Generator().manual_seed(22)).to(F16).to(DEV)
+    n0 = _capi.launch_count()
+    _, dq, dk, dv = grads(q, k, v, d_o, True, None, True)
+    assert _capi.launch_count() == n0 + 1 + 4
+    bhnd = lambda t: t.transpose(1, 2)  # noqa: E731
+    ref, b16 = truth(bhnd(q), bhnd(k), bhnd(v), bhnd(d_o), True)
+    assert_grads(tuple(bhnd(t) for t in (dq, dk, dv)), ref, b16, F16, "BNHD packed views, D=160")
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_wide_backward_agrees_with_the_generic_cuda_core_backward(causal):
     """fa_set_bwd_kernel(3) forces the CUDA-core kernels at head dims 129..256 too: two independent implementations
