@@ -1413,18 +1413,19 @@ int fa_umma_selftest(const void* a, const void* b, float* out, int dtype, int mo
                      uint32_t sbo, void* stream) {
   if (a == nullptr || b == nullptr || out == nullptr)
     return fail(FA_ERR_INVALID_ARG, "a, b and out must not be null");
-  if (mode < 0 || mode > 4) return fail(FA_ERR_INVALID_ARG, "mode must be 0..4");
+  if (mode < 0 || mode > 5) return fail(FA_ERR_INVALID_ARG, "mode must be 0..5");
   if (dtype != FA_DTYPE_F16 && dtype != FA_DTYPE_BF16)
     return fail(FA_ERR_INVALID_ARG, "dtype must be FA_DTYPE_F16 or FA_DTYPE_BF16");
   int dev;
   int rc = check_device(&dev);
   if (rc) return rc;
   if (lbo == 0 && sbo == 0) { lbo = 16384; sbo = 1024; }
+  if (mode == 5) lbo = 0xE5u;  // marks the extra un-swizzled k-step for the kernel (mode 5 = mode 0 + that step)
   const int64_t st[4] = {128 * 128, 128 * 128, 128, 1};
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, a, 1, 1, 128, 128, st, dtype, 128))) return rc;
   if ((rc = make_map(&mb, b, 1, 1, 128, 128, st, dtype, 128))) return rc;
-  const int smem = 65536 + 128 + 1024;
+  const int smem = 65536 + 128 + 1024 + 8192;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == FA_DTYPE_BF16) {
     if ((rc = set_smem(fa::umma_probe_kernel<true>, smem))) return rc;

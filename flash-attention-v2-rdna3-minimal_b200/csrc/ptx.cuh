@@ -463,6 +463,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices (row r of a core matrix at +16 r bytes); `lbo_bytes` is the
+// distance between the core matrices of one row group along K, `sbo_bytes` between row groups (8 rows) along M / N.
+// Used for the one-k-step "bias" operands of the backward (a ones column against a column of -L_i / -D_i); pinned on the
+// hardware by fa_umma_selftest mode 5.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
 // The same descriptor as two 32-bit halves.  The high word depends only on the layout (SBO,
 // version, swizzle), so it is a compile-time constant; the low word is the 14-bit address field
 // plus LBO << 16, and stepping the operand by `bytes` inside one tile is `lo + (bytes >> 4)` (no
@@ -470,6 +483,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 // registers makes one tcgen05.mma cost a single UIADD3 + UTCHMMA on the issuing thread.
 __host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi_nosw(uint32_t sbo_bytes) {  // high word of make_smem_desc_nosw
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
 }
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);

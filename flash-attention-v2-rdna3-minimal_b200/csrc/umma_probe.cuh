@@ -53,6 +53,26 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // mode 5 = mode 0 plus ONE more k-step whose operands are un-swizzled K-major [128 rows][16 columns] tiles written by
+  // the threads: A_ext = (1, 2, 0, ...) in every row, B_ext row n = (bias0[n], bias1[n], 0, ...), the second 16-byte
+  // k-chunk of both aliased onto a shared block of zeros through the descriptor's LBO: out = A B^T + bias0[n] + 2 bias1[n]
+  uint8_t* sExt = smem + 65536 + 1024;  // A_ext 2 KB | B_ext 2 KB | zeros 2 KB
+  if (mode == 5) {
+    const bool bf = kBF16;
+    auto cvt = [&](float x) -> uint32_t {
+      return bf ? static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16(x)))
+                : static_cast<uint32_t>(__half_as_ushort(__float2half(x)));
+    };
+    const uint32_t off = (tid >> 3) * 128 + (tid & 7) * 16;
+    *reinterpret_cast<uint4*>(sExt + off) = make_uint4(cvt(1.f) | (cvt(2.f) << 16), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sExt + 2048 + off) =
+        make_uint4(cvt((tid - 64) * 0.125f) | (cvt((tid % 7) * 0.25f) << 16), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sExt + 4096 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  if (mode == 5) mode = 0;
+  const bool ext_step = (sExt != nullptr) && (lbo_b == 0xE5u);  // (set by the host for mode 5)
+
   if (tid == 0) {
     const bool a_tma = (mode == 0 || mode == 1 || mode == 4);
     mbar_arrive_expect_tx(bar_load, a_tma ? 65536 : 32768);
@@ -112,6 +132,10 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmap_a,
       } else {
         umma_ss(tmem, a_desc, b_desc, idesc, k > 0);
       }
+    }
+    if (ext_step) {
+      const uint32_t e = smem_u32(sExt);
+      umma_ss(tmem, make_smem_desc_nosw(e, 4096, 128), make_smem_desc_nosw(e + 2048, 2048, 128), idesc, 1);
     }
     tc_commit(bar_mma);
   }
