@@ -38,7 +38,9 @@ int fa_set_bwd_kernel(int kernel);
 /*
  * UMMA / TMA / TMEM self-test: computes one 128x128x128 product through the same operand paths the
  * attention kernels use (mode 0: A.B^T both K-major; 1: A.B with B MN-major; 2: A from TMEM;
- * 3: A written to smem by threads; 4: A^T.B with A and B MN-major, the backward's dV/dK products).
+ * 3: A written to smem by threads; 4: A^T.B with A and B MN-major, the backward's dV/dK products;
+ * 5: mode 0 plus one more k-step from UN-swizzled K-major [128][16] tiles whose second k-chunk aliases a shared zeros block
+ * through the descriptor's LBO - out = A.B^T + bias0[n] + 2 bias1[n], bias0[n] = (n-64)/8, bias1[n] = (n%7)/4).
  * a, b: device [128,128] 16-bit row-major; out: device
  * [128,128] fp32.  lbo/sbo: B-descriptor byte offsets for modes 1-3 (0,0 = the values the kernels
  * use).  Counterpart of the reference's gemm_test/ micro-kernels.
