@@ -182,16 +182,20 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
       mbar_wait(bar_str(s), (it / kS) & 1, 81);
       tc_fence_after();
       const uint32_t t1 = sStr + s * 2 * L::kStrBytes, t2 = t1 + L::kStrBytes;
+      // split descriptors (ptx.cuh): the high word is a constant, stepping an operand is one add on the low word
+      constexpr uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t r1_lo = smem_desc_lo(sRes1, 16), t1_lo = smem_desc_lo(t1, 16);
 #pragma unroll
       for (int k = 0; k < kKSteps; ++k) {
-        umma_ss(tmem + kColS, make_smem_desc_sw128(sRes1 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                make_smem_desc_sw128(t1 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+        umma_ss2(tmem + kColS, r1_lo + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), desc_hi,
+                 t1_lo + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), desc_hi, idesc_s, k > 0);
       }
       if (kMode != kBwdWideDV) {
+        const uint32_t r2_lo = smem_desc_lo(sRes2, 16), t2_lo = smem_desc_lo(t2, 16);
 #pragma unroll
         for (int k = 0; k < kKSteps; ++k) {
-          umma_ss(tmem + kColP, make_smem_desc_sw128(sRes2 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(t2 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_s, k > 0);
+          umma_ss2(tmem + kColP, r2_lo + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), desc_hi,
+                   t2_lo + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), desc_hi, idesc_s, k > 0);
         }
       }
       tc_commit(bar_mma1);
@@ -249,10 +253,11 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
     if (tid == 0) {
       tc_fence_after();
       const uint32_t t_out = sStr + s * 2 * L::kStrBytes + ((kMode == kBwdWideDV) ? L::kStrBytes : 0);
+      const uint32_t out_lo = smem_desc_lo(t_out, 8192);
 #pragma unroll
       for (int ks = 0; ks < kWideT / 16; ++ks) {  // contraction over the 64 streamed rows
-        umma_ts(tmem + kColAcc, tmem + kColA + ks * 8, make_smem_desc_sw128(t_out + ks * 2048, 8192, 1024), idesc_o,
-                (it > 0) || (ks > 0));
+        umma_ts2(tmem + kColAcc, tmem + kColA + ks * 8, out_lo + ((ks * 2048) >> 4), smem_desc_hi_sw128(1024), idesc_o,
+                 (it > 0) || (ks > 0));
       }
       tc_commit(bar_mma2);
       if (kS == 1 && it + 1 < n_iter) {  // one stage: the next tile pair can only be fetched now
