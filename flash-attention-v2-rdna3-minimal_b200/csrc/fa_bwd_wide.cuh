@@ -10,6 +10,8 @@
 //   mode dV : CTA = 128 keys.   per 64-query tile:  S^T = K Q^T                 P^T        ->  dV += P^T dO
 //   mode dK : CTA = 128 keys.   per 64-query tile:  S^T = K Q^T, dP^T = V dO^T  dS^T       ->  dK += dS^T Q
 //   mode dQ : CTA = 128 queries per 64-key tile:    S = Q K^T,   dP = dO V^T    dS         ->  dQ += dS K
+//   mode dKV: modes dV and dK in ONE launch where two 128 x D accumulators fit next to the scores (D <= 192: 128 + 2 x 192 = 512
+//             TMEM columns): S^T, P^T and the Q / dO tiles are computed / fetched once (4 GEMMs per tile instead of 5)
 //
 // with P = 2^(S c - L), dS = P o (dP - D) (kernel_fp16.cu:698-737).  In every mode the CTA's own 128 rows ("resident":
 // K,V or Q,dO) are TMEM lanes, the other operand streams through shared memory in 64-row tiles, the 16-bit P / dS goes
@@ -22,13 +24,14 @@
 // barriers; the streamed tiles are double-buffered where shared memory allows): a first tensor-core version, ~500x
 // the CUDA-core kernels it replaces, not yet pipelined like fa_bwd_ws.cuh.
 //
-// TMEM: scores [0,64), dP [64,128), accumulator [128,128+D), 16-bit P/dS [384,416).
+// TMEM: scores [0,64), dP [64,128), accumulator [128,128+D) (mode dKV: dV there, dK at [128+D,128+2D)).  The 16-bit P / dS tile
+// lives INSIDE the score columns: thread (row, half) packs its 32 columns [32 half, 32 half + 32) into the first 16 of them.
 #pragma once
 #include "fa_bwd_tc.cuh"
 
 namespace fa {
 
-constexpr int kBwdWideDV = 0, kBwdWideDK = 1, kBwdWideDQ = 2;
+constexpr int kBwdWideDV = 0, kBwdWideDK = 1, kBwdWideDQ = 2, kBwdWideDKV = 3;
 constexpr int kBwdWideThreads = 256;
 constexpr int kWideT = 64;  // rows of a streamed tile
 
@@ -36,6 +39,7 @@ template <int kDP, int kMode>
 struct BwdWideSmem {
   static constexpr int kResBytes = kTileM * kDP * 2;  // one resident tile [128][kDP]
   static constexpr int kStrBytes = kWideT * kDP * 2;  // one streamed tile [64][kDP]
+  static_assert(kMode != kBwdWideDKV || kDP <= 192, "two accumulators need 128 + 2 kDP <= 512 TMEM columns");
   static constexpr int kNumRes = (kMode == kBwdWideDV) ? 1 : 2;
   static constexpr int kStages = (kNumRes * kResBytes + 2 * 2 * kStrBytes <= 222 * 1024) ? 2 : 1;
   static constexpr int kRes = 0;
@@ -60,13 +64,16 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
                    const __grid_constant__ CUtensorMap tmap_str1,  // Q (dV, dK) | K (dQ), box {64, 64}
                    const __grid_constant__ CUtensorMap tmap_str2,  // dO (dV, dK) | V (dQ)
                    const __grid_constant__ CUtensorMap tmap_out,   // dV | dK | dQ, box {64, 128}
+                   const __grid_constant__ CUtensorMap tmap_out2,  // mode dKV: dK (tmap_out is dV); unused otherwise
                    const BwdWideParams p) {
   using L = BwdWideSmem<kDP, kMode>;
   constexpr int kS = L::kStages;
   constexpr int kDBlocks = kDP / 64;
   constexpr int kKSteps = kDP / 16;  // contraction over the head dim (scores)
   constexpr bool kVecLD = (kMode != kBwdWideDQ);  // L, D are vectors over the streamed queries
-  constexpr uint32_t kColS = 0, kColP = 64, kColAcc = 128, kColA = 384;
+  constexpr bool kTwoOut = (kMode == kBwdWideDKV);
+  constexpr bool kNeedDP = (kMode != kBwdWideDV);
+  constexpr uint32_t kColS = 0, kColP = 64, kColAcc = 128, kColAcc2 = 128 + kDP;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -110,6 +117,7 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
     tma_prefetch_desc(&tmap_str1);
     tma_prefetch_desc(&tmap_str2);
     tma_prefetch_desc(&tmap_out);
+    if (kTwoOut) tma_prefetch_desc(&tmap_out2);
 #pragma unroll
     for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
@@ -190,7 +198,7 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
         umma_ss2(tmem + kColS, r1_lo + (((k >> 2) * 16384 + (k & 3) * 32) >> 4), desc_hi,
                  t1_lo + (((k >> 2) * 8192 + (k & 3) * 32) >> 4), desc_hi, idesc_s, k > 0);
       }
-      if (kMode != kBwdWideDV) {
+      if (kNeedDP) {
         const uint32_t r2_lo = smem_desc_lo(sRes2, 16), t2_lo = smem_desc_lo(t2, 16);
 #pragma unroll
         for (int k = 0; k < kKSteps; ++k) {
@@ -217,12 +225,12 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
     {
       uint32_t sv[32], dv[32];
       tmem_ld_x32(tmem + lane_base + kColS + half * 32, sv);
-      if (kMode != kBwdWideDV) tmem_ld_x32(tmem + lane_base + kColP + half * 32, dv);
+      if (kNeedDP) tmem_ld_x32(tmem + lane_base + kColP + half * 32, dv);
       tmem_wait_ld();
-      uint32_t pk[16];
+      uint32_t pk[16], pk2[16];
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        float val[2];
+        float val[2], val2[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int col = half * 32 + e + u;
@@ -235,16 +243,21 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
             const bool ok = key < p.Nkv && qrow < p.Nq && (!kCausal || key <= qrow);
             pe = ok ? pe : 0.f;
           }
-          if (kMode == kBwdWideDV) {
-            val[u] = pe;
-          } else {
+          val[u] = pe;
+          val2[u] = 0.f;
+          if (kNeedDP) {
             const float dq_ = kVecLD ? sLD[64 + col] : d_lane;
-            val[u] = pe * (__uint_as_float(dv[e + u]) - dq_);
+            const float ds = pe * (__uint_as_float(dv[e + u]) - dq_);
+            if (kTwoOut) val2[u] = ds; else val[u] = ds;
           }
         }
         pk[e >> 1] = pack2<kBF16>(val[0], val[1]);
+        if (kTwoOut) pk2[e >> 1] = pack2<kBF16>(val2[0], val2[1]);
       }
-      tmem_st_x16(tmem + lane_base + kColA + half * 16, pk);
+      // the 16-bit tile over the first 16 of my own 32 score columns (P, or dS in the one-output dK / dQ modes); mode dKV
+      // puts dS over my dP columns likewise
+      tmem_st_x16(tmem + lane_base + kColS + half * 32, pk);
+      if (kTwoOut) tmem_st_x16(tmem + lane_base + kColP + half * 32, pk2);
       tmem_wait_st();
     }
     tc_fence_before();
@@ -252,12 +265,22 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
 
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t t_out = sStr + s * 2 * L::kStrBytes + ((kMode == kBwdWideDV) ? L::kStrBytes : 0);
-      const uint32_t out_lo = smem_desc_lo(t_out, 8192);
+      // k-step ks covers streamed rows [16 ks, 16 ks + 16): 16-bit A columns 32 (ks / 2) + 8 (ks % 2) of the score tile
+      const uint32_t t_first = sStr + s * 2 * L::kStrBytes;  // Q | K
+      const uint32_t t_second = t_first + L::kStrBytes;       // dO | V
+      const uint32_t out_lo = smem_desc_lo((kMode == kBwdWideDV || kTwoOut) ? t_second : t_first, 8192);
 #pragma unroll
       for (int ks = 0; ks < kWideT / 16; ++ks) {  // contraction over the 64 streamed rows
-        umma_ts2(tmem + kColAcc, tmem + kColA + ks * 8, out_lo + ((ks * 2048) >> 4), smem_desc_hi_sw128(1024), idesc_o,
-                 (it > 0) || (ks > 0));
+        umma_ts2(tmem + kColAcc, tmem + kColS + (ks >> 1) * 32 + (ks & 1) * 8, out_lo + ((ks * 2048) >> 4),
+                 smem_desc_hi_sw128(1024), idesc_o, (it > 0) || (ks > 0));
+      }
+      if (kTwoOut) {  // dK += dS^T Q
+        const uint32_t out2_lo = smem_desc_lo(t_first, 8192);
+#pragma unroll
+        for (int ks = 0; ks < kWideT / 16; ++ks) {
+          umma_ts2(tmem + kColAcc2, tmem + kColP + (ks >> 1) * 32 + (ks & 1) * 8, out2_lo + ((ks * 2048) >> 4),
+                   smem_desc_hi_sw128(1024), idesc_o, (it > 0) || (ks > 0));
+        }
       }
       tc_commit(bar_mma2);
       if (kS == 1 && it + 1 < n_iter) {  // one stage: the next tile pair can only be fetched now
@@ -278,34 +301,42 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
   }
   __syncthreads();
   tc_fence_after();
-  uint8_t* stage = smem + L::kRes;
   constexpr int kHalfD = kDP / 2;
+  auto acc_to_stage = [&](uint32_t col_acc, uint8_t* stage, float out_scale) {
 #pragma unroll 1
-  for (int cidx = 0; cidx < kHalfD / 32; ++cidx) {
-    uint32_t a[32];
-    if (n_iter > 0) {
-      tmem_ld_x32(tmem + lane_base + kColAcc + half * kHalfD + cidx * 32, a);
-      tmem_wait_ld();
-    } else {
+    for (int cidx = 0; cidx < kHalfD / 32; ++cidx) {
+      uint32_t a[32];
+      if (n_iter > 0) {
+        tmem_ld_x32(tmem + lane_base + col_acc + half * kHalfD + cidx * 32, a);
+        tmem_wait_ld();
+      } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) a[e] = 0u;
-    }
+        for (int e = 0; e < 32; ++e) a[e] = 0u;
+      }
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      uint4 vv;
-      vv.x = pack2<kBF16>(__uint_as_float(a[ch * 8 + 0]) * p.out_scale, __uint_as_float(a[ch * 8 + 1]) * p.out_scale);
-      vv.y = pack2<kBF16>(__uint_as_float(a[ch * 8 + 2]) * p.out_scale, __uint_as_float(a[ch * 8 + 3]) * p.out_scale);
-      vv.z = pack2<kBF16>(__uint_as_float(a[ch * 8 + 4]) * p.out_scale, __uint_as_float(a[ch * 8 + 5]) * p.out_scale);
-      vv.w = pack2<kBF16>(__uint_as_float(a[ch * 8 + 6]) * p.out_scale, __uint_as_float(a[ch * 8 + 7]) * p.out_scale);
-      *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kHalfD + cidx * 32 + ch * 8)) = vv;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 vv;
+        vv.x = pack2<kBF16>(__uint_as_float(a[ch * 8 + 0]) * out_scale, __uint_as_float(a[ch * 8 + 1]) * out_scale);
+        vv.y = pack2<kBF16>(__uint_as_float(a[ch * 8 + 2]) * out_scale, __uint_as_float(a[ch * 8 + 3]) * out_scale);
+        vv.z = pack2<kBF16>(__uint_as_float(a[ch * 8 + 4]) * out_scale, __uint_as_float(a[ch * 8 + 5]) * out_scale);
+        vv.w = pack2<kBF16>(__uint_as_float(a[ch * 8 + 6]) * out_scale, __uint_as_float(a[ch * 8 + 7]) * out_scale);
+        *reinterpret_cast<uint4*>(stage + sw128_offset_16bit(r, half * kHalfD + cidx * 32 + ch * 8)) = vv;
+      }
     }
-  }
+  };
+  uint8_t* stage = smem + L::kRes;                  // the first resident tile
+  uint8_t* stage2 = smem + L::kRes + L::kResBytes;  // mode dKV: the second one (dK)
+  acc_to_stage(kColAcc, stage, kTwoOut ? 1.f : p.out_scale);
+  if (kTwoOut) acc_to_stage(kColAcc2, stage2, p.out_scale);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
-    for (int db = 0; db < kDBlocks; ++db) tma_store_4d(&tmap_out, smem_u32(stage) + db * 16384, db * 64, row0, h, b);
+    for (int db = 0; db < kDBlocks; ++db) {
+      tma_store_4d(&tmap_out, smem_u32(stage) + db * 16384, db * 64, row0, h, b);
+      if (kTwoOut) tma_store_4d(&tmap_out2, smem_u32(stage2) + db * 16384, db * 64, row0, h, b);
+    }
     tma_store_commit();
     tma_store_wait_read();
   }

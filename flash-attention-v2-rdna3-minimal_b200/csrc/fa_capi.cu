@@ -760,11 +760,13 @@ int launch_bwd_wide_mode(const BwdMaps& m, const fa::BwdWideParams& wp, int B, i
   int rc = set_smem(kernel, smem, &configured, device);
   if (rc) return rc;
   if (kMode == fa::kBwdWideDV)
-    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.k, m.q64, m.do64, m.dv, wp);
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.k, m.q64, m.do64, m.dv, m.dv, wp);
   else if (kMode == fa::kBwdWideDK)
-    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.v, m.q64, m.do64, m.dk, wp);
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.v, m.q64, m.do64, m.dk, m.dk, wp);
+  else if (kMode == fa::kBwdWideDKV)
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.k, m.v, m.q64, m.do64, m.dv, m.dk, wp);
   else
-    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.q, m.d_o, m.k64, m.v64, m.dq16, wp);
+    kernel<<<grid, fa::kBwdWideThreads, smem, stream>>>(m.q, m.d_o, m.k64, m.v64, m.dq16, m.dq16, wp);
   FA_CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
@@ -775,10 +777,16 @@ template <int kDP, bool kBF16, bool kCausal>
 int launch_bwd_wide(const BwdMaps& m, fa::BwdWideParams wp, int B, int H, int Nq, int Nkv, float scale, int device,
                     cudaStream_t stream) {
   int rc;
-  wp.out_scale = 1.f;
-  if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDV>(m, wp, B, H, Nkv, device, stream))) return rc;
+  if constexpr (kDP <= 192) {  // dV and dK in one launch: both accumulators fit in tensor memory next to the scores
+    wp.out_scale = scale;
+    if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDKV>(m, wp, B, H, Nkv, device, stream))) return rc;
+  } else {
+    wp.out_scale = 1.f;
+    if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDV>(m, wp, B, H, Nkv, device, stream))) return rc;
+    wp.out_scale = scale;
+    if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDK>(m, wp, B, H, Nkv, device, stream))) return rc;
+  }
   wp.out_scale = scale;
-  if ((rc = launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDK>(m, wp, B, H, Nkv, device, stream))) return rc;
   return launch_bwd_wide_mode<kDP, kBF16, kCausal, fa::kBwdWideDQ>(m, wp, B, H, Nq, device, stream);
 }
 

@@ -126,8 +126,8 @@ int fa_host_sync(void);
  *                (what the reference recomputes in every CTA, kernel_fp16.cu:605-631)
  *
  * Kernels: D % 8 == 0 with 16-byte aligned pointers and strides runs on the tensor cores - D <= 128: pre-pass, the pipelined
- * kernel fa_bwd_ws.cuh, dQ conversion (3 launches); 128 < D <= 256: pre-pass + one launch each for dV, dK and dQ of
- * fa_bwd_wide.cuh (4 launches, dQ written directly).  Everything else the forward accepts (D up to 1024, any alignment) runs
+ * kernel fa_bwd_ws.cuh, dQ conversion (3 launches); 128 < D <= 256: pre-pass + fa_bwd_wide.cuh, dQ written directly (D <= 192: one
+ * launch for dV and dK together and one for dQ, 3 launches; above: one each, 4 launches).  Everything else the forward accepts (D up to 1024, any alignment) runs
  * the generic CUDA-core kernels (pre-pass + 2 launches).  D > 1024 returns FA_ERR_UNSUPPORTED.  Innermost strides must be 1.
  * All launches go to `stream`, asynchronous with respect to the host.
  */

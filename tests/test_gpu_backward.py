@@ -209,9 +209,11 @@ WIDE_BWD_SHAPES = [
 ]
 
 
-def _is_wide_tc(D):
+def _bwd_launches(D):
+    """Launches of one backward call: pre-pass + (dV/dK fused + dQ at head dims 129..192 | dV + dK + dQ at 193..256 of the
+    three-launch tcgen05 kernel | dQ kernel + dK/dV kernel of the generic path above 256 or off the 8-element grid)."""
     DP = -(-D // 8) * 8
-    return 128 < DP <= 256
+    return 1 + (2 if 128 < DP <= 192 else 3 if 192 < DP <= 256 else 2)
 
 
 @pytest.mark.parametrize("causal", [False, True])
@@ -225,8 +227,7 @@ def test_backward_head_dims_above_128_match_fp32_autograd(shape, dtype, causal):
     ref, b16 = truth(q, k, v, d_o, causal)
     n0 = _capi.launch_count()
     _, dq, dk, dv = grads(q.to(DEV), k.to(DEV), v.to(DEV), d_o.to(DEV), causal)
-    # forward; pre-pass + (dV, dK, dQ launches of the tcgen05 kernel | dQ kernel, dK/dV kernel of the generic path)
-    assert _capi.launch_count() == n0 + 1 + (4 if _is_wide_tc(D) else 3)
+    assert _capi.launch_count() == n0 + 1 + _bwd_launches(D)  # forward + backward
     assert_grads((dq, dk, dv), ref, b16, dtype, f"{shape} {dtype} causal={causal}")
 
 
@@ -239,7 +240,7 @@ def test_wide_backward_bnhd_layout_and_packed_qkv_views():
     d_o = torch.rand((B, N, H, D), generator=torch.Generator().manual_seed(22)).to(F16).to(DEV)
     n0 = _capi.launch_count()
     _, dq, dk, dv = grads(q, k, v, d_o, True, None, True)
-    assert _capi.launch_count() == n0 + 1 + 4
+    assert _capi.launch_count() == n0 + 1 + _bwd_launches(D)
     bhnd = lambda t: t.transpose(1, 2)  # noqa: E731
     ref, b16 = truth(bhnd(q), bhnd(k), bhnd(v), bhnd(d_o), True)
     assert_grads(tuple(bhnd(t) for t in (dq, dk, dv)), ref, b16, F16, "BNHD packed views, D=160")
