@@ -43,6 +43,7 @@ struct BwdParams {
   float scale_log2;    // scale * log2(e)
   float scale;
   int lpt_group;       // fa_bwd_ws.cuh, causal: (batch, head) pairs per longest-first group of the 1-D grid
+  unsigned long long* trace;  // debug builds only (-DFA_TRACE): clock64() stamps of one CTA (tools/trace_bwd.py)
 };
 
 template <int kDP>

@@ -30,6 +30,17 @@
 namespace fa {
 
 constexpr int kBwdWsThreads = 512;
+
+// Debug-only timeline (-DFA_TRACE, never in the shipped library): lane 0 of the MMA warp (role 0), of P / dS warp 0 (role 1)
+// and of drain warp 8 (role 2) stamps clock64() into p.trace[role][iteration][event] for one CTA; tools/trace_bwd.py.
+#ifdef FA_TRACE
+#define FA_BTR(role, it, ev)                                                                      \
+  do {                                                                                            \
+    if (btr_on && lane == 0 && (it) < 128) p.trace[((role) * 128 + (it)) * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FA_BTR(role, it, ev) do { } while (0)
+#endif
 #ifndef FA_BWD_EXP_NO_LD
 #define FA_BWD_EXP_NO_LD 0
 #endif
@@ -117,6 +128,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int i_begin = kCausal ? min(j, i_end) : 0;  // query tiles above the diagonal see no key of j
   const int n_iter = i_end - i_begin;
   const int64_t bh = static_cast<int64_t>(b) * p.H + h;
+#ifdef FA_TRACE
+  const bool btr_on = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 &&
+                      (warp == 12 || warp == 0 || warp == 8);
+#endif
 
   if (tid == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128-byte-swizzled tiles need a 1024-byte-aligned base
@@ -198,21 +213,26 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t q_mn = smem_desc_lo(sQ + buf * L::kTileBytes, 16384);
           // k-step ks covers queries [16 ks, 16 ks + 16): 16-bit A columns of half ks/4 at 64 (ks/4) + 8 (ks%4) of the
           // S^T / dP^T accumulator; B rows 16 ks of the dO / Q tile
+          FA_BTR(0, it, 0);
           mbar_wait(bar_p_ready, it & 1, 63);
           tc_fence_after();
+          FA_BTR(0, it, 1);
 #pragma unroll
           for (int ks = 0; ks < kTileM / 16; ++ks) {  // dV += P^T dO_i
             umma_ts2(tmem + kColdV, tmem + kColS + (ks >> 2) * 64 + (ks & 3) * 8, do_mn + ((ks * 2048) >> 4), desc_hi,
                      idesc_t, (it > 0) || (ks > 0));
           }
           tc_commit(bar_do_free);
+          FA_BTR(0, it, 2);
           if (it + 1 < n_iter) {  // in order behind dV(i), which read P^T from these columns
             mbar_wait(bar_q_full(buf ^ 1), ((it + 1) >> 1) & 1, 64);
             tc_fence_after();
             issue_s(it + 1);
           }
+          FA_BTR(0, it, 3);
           mbar_wait(bar_ds_ready, it & 1, 65);
           tc_fence_after();
+          FA_BTR(0, it, 4);
 #pragma unroll
           for (int ks = 0; ks < kTileM / 16; ++ks) {  // dK += dS^T Q_i
             umma_ts2(tmem + kColdK, tmem + kColdP + (ks >> 2) * 64 + (ks & 3) * 8, q_mn + ((ks * 2048) >> 4), desc_hi,
@@ -225,11 +245,14 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
                      k > 0);
           }
           tc_commit(bar_dq);
+          FA_BTR(0, it, 5);
           if (it + 1 < n_iter) {
             mbar_wait(bar_do_full, (it + 1) & 1, 66);
             mbar_wait(bar_drained, it & 1, 67);  // dQ(i) has left the dP^T columns
             tc_fence_after();
+            FA_BTR(0, it, 6);
             issue_dp();
+            FA_BTR(0, it, 7);
           }
         }
       }
@@ -310,8 +333,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
       const int i = i_begin + it;
+      FA_BTR(2, it, 0);
       mbar_wait(bar_dq, it & 1, 70);
       tc_fence_after();
+      FA_BTR(2, it, 1);
       uint32_t v[kDP];
 #pragma unroll
       for (int cidx = 0; cidx < kDP / 32; ++cidx) tmem_ld_x32(tmem + lane_base + kColdQ + cidx * 32, v + cidx * 32);
@@ -319,6 +344,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_drained);
+      FA_BTR(2, it, 2);
       // registers -> this warp's swizzled fp32 staging tile [32 rows][32 columns] -> TMA reduce-add into
       // dq_acc[b,h, 32 rows, 32 columns] (rows >= Nq are clipped by the tensor map)
 #pragma unroll
@@ -367,8 +393,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const bool need_mask = (kCausal && i == j) || (key0 + kTileN > p.Nkv) || ((i + 1) * kTileM > p.Nq);
 
       // ---- phase A: P^T = 2^(S^T c - L) for my 64 queries; 16-bit copy over the S^T columns
+      FA_BTR(1, it, 0);
       mbar_wait(bar_ld_full(it & 1), (it >> 1) & 1, 71);
       mbar_wait(bar_s, par, 72);
+      FA_BTR(1, it, 1);
       tc_fence_after();
       float pf[64];
 #pragma unroll
@@ -378,14 +406,20 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_ld_x32(tmem + lane_base + kColS + qb, sv);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float pe = ex2_approx(fmaf(__uint_as_float(sv[e]), c, -sL[FA_LD_IDX(qb + e)]));
-          if (need_mask) {
+        for (int e = 0; e < 32; e += 2) {  // S c - L, two elements per instruction (FFMA2)
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]), c, c, -sL[FA_LD_IDX(qb + e)],
+                -sL[FA_LD_IDX(qb + e + 1)]);
+          pf[q2 * 32 + e] = ex2_approx(x0);
+          pf[q2 * 32 + e + 1] = ex2_approx(x1);
+        }
+        if (need_mask) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
             const int qrow = i * kTileM + qb + e;
             const bool ok = key_ok && qrow < p.Nq && (!kCausal || key <= qrow);
-            pe = ok ? pe : 0.f;
+            pf[q2 * 32 + e] = ok ? pf[q2 * 32 + e] : 0.f;
           }
-          pf[q2 * 32 + e] = pe;
         }
         uint32_t pk[16];
 #pragma unroll
@@ -396,22 +430,34 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_ready);
+      FA_BTR(1, it, 2);
 
       // ---- phase B: dS^T = P^T o (dP^T - D); 16-bit copy over the dP^T columns (A of dK) and, as my row of the
       // [key][query] shared-memory tile (A of dQ_i = dS K_j, MN-major)
+      // (the D values of my first 32 queries are fetched BEFORE the wait: the pass below is on the kernel's critical loop -
+      // dP^T -> dS -> dK, dQ -> drain -> next dP^T - and its shared-memory reads compete with the operand reads of the
+      // products running at that time)
+      float d_first[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) d_first[e] = sD[FA_LD_IDX(half * 64 + e)];
       mbar_wait(bar_dp, par, 73);
       tc_fence_after();
+      FA_BTR(1, it, 3);
 #pragma unroll
       for (int q2 = 0; q2 < 2; ++q2) {
         const int qb = half * 64 + q2 * 32;
         uint32_t dv[32];
         tmem_ld_x32(tmem + lane_base + kColdP + qb, dv);
         tmem_wait_ld();
+        if (q2 == 0) FA_BTR(1, it, 5); else FA_BTR(1, it, 7);
         uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float d0 = pf[q2 * 32 + e] * (__uint_as_float(dv[e]) - sD[FA_LD_IDX(qb + e)]);
-          const float d1 = pf[q2 * 32 + e + 1] * (__uint_as_float(dv[e + 1]) - sD[FA_LD_IDX(qb + e + 1)]);
+        for (int e = 0; e < 32; e += 2) {  // dS = P (dP - D), two elements per instruction (FADD2 / FMUL2)
+          const float dd0 = (q2 == 0) ? d_first[e] : sD[FA_LD_IDX(qb + e)];
+          const float dd1 = (q2 == 0) ? d_first[e + 1] : sD[FA_LD_IDX(qb + e + 1)];
+          float d0, d1;
+          fsub2(d0, d1, __uint_as_float(dv[e]), __uint_as_float(dv[e + 1]), dd0, dd1);
+          fmul2(d0, d1, d0, d1, pf[q2 * 32 + e], pf[q2 * 32 + e + 1]);
           pk[e >> 1] = pack2<kBF16>(d0, d1);
         }
         tmem_st_x16(tmem + lane_base + kColdP + half * 64 + q2 * 16, pk);
@@ -419,6 +465,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int ch = 0; ch < 4; ++ch)
           *reinterpret_cast<uint4*>(smem + L::kdS + sw128_offset_16bit(r, qb + ch * 8)) =
               make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        if (q2 == 0) FA_BTR(1, it, 6);
       }
       tmem_wait_st();
       fence_proxy_async_smem();
@@ -428,6 +475,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         mbar_arrive(bar_ds_ready);
         mbar_arrive(bar_ld_free(it & 1));
       }
+      FA_BTR(1, it, 4);
     }
 
     // ---- epilogue: dV and scale * dK (TMEM lane = key row) -> 16 bit -> swizzled smem (the two Q buffers) -> TMA

@@ -1380,7 +1380,10 @@ int fa_bwd_sm100(const void* q, const void* k, const void* v, const void* o, con
     fa::BwdWideParams wp{lse, delta, Nq, Nkv, H, scale * 1.4426950408889634f, 1.f};
     return dispatch_bwd_wide(m, wp, B, H, Nq, Nkv, D, dtype, causal, scale, dev, st);
   }
-  fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale, 1};
+  fa::BwdParams bp{lse, delta, dq_accum, Nq, Nkv, H, D, scale * 1.4426950408889634f, scale, 1, nullptr};
+#ifdef FA_TRACE
+  bp.trace = g_trace;
+#endif
   if ((rc = dispatch_bwd_tc(m, bp, B, H, Nkv, D, dtype, causal, dev, st))) return rc;
 
   // 3. dQ = scale * dq_accum
