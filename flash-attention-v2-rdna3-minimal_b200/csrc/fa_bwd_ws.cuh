@@ -286,8 +286,9 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
             lv[e] = ok ? p.lse[bh * p.Nq + row0 + e] : 0.f;
             dv[e] = ok ? p.delta[bh * p.Nq + row0 + e] : 0.f;
           }
-          *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(lv[0], lv[1], lv[2], lv[3]);
-          *reinterpret_cast<float4*>(dst + 128 + lane * 4) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+          // (negated: the consumers compute S c + (-L) and dP + (-D) with packed adds, which take no negate modifier)
+          *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(-lv[0], -lv[1], -lv[2], -lv[3]);
+          *reinterpret_cast<float4*>(dst + 128 + lane * 4) = make_float4(-dv[0], -dv[1], -dv[2], -dv[3]);
           mbar_arrive(bar_ld_full(it & 1));
         };
         if (lane == 0) {
@@ -406,10 +407,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_ld_x32(tmem + lane_base + kColS + qb, sv);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {  // S c - L, two elements per instruction (FFMA2)
+        for (int e = 0; e < 32; e += 2) {  // S c + (-L), two elements per instruction (FFMA2; sL holds -L, sD holds -D)
           float x0, x1;
-          ffma2(x0, x1, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]), c, c, -sL[FA_LD_IDX(qb + e)],
-                -sL[FA_LD_IDX(qb + e + 1)]);
+          ffma2(x0, x1, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]), c, c, sL[FA_LD_IDX(qb + e)],
+                sL[FA_LD_IDX(qb + e + 1)]);
           pf[q2 * 32 + e] = ex2_approx(x0);
           pf[q2 * 32 + e + 1] = ex2_approx(x1);
         }
@@ -452,11 +453,11 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (q2 == 0) FA_BTR(1, it, 5); else FA_BTR(1, it, 7);
         uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {  // dS = P (dP - D), two elements per instruction (FADD2 / FMUL2)
+        for (int e = 0; e < 32; e += 2) {  // dS = P (dP + (-D)), two elements per instruction (FADD2 / FMUL2)
           const float dd0 = (q2 == 0) ? d_first[e] : sD[FA_LD_IDX(qb + e)];
           const float dd1 = (q2 == 0) ? d_first[e + 1] : sD[FA_LD_IDX(qb + e + 1)];
           float d0, d1;
-          fsub2(d0, d1, __uint_as_float(dv[e]), __uint_as_float(dv[e + 1]), dd0, dd1);
+          fadd2(d0, d1, __uint_as_float(dv[e]), __uint_as_float(dv[e + 1]), dd0, dd1);
           fmul2(d0, d1, d0, d1, pf[q2 * 32 + e], pf[q2 * 32 + e + 1]);
           pk[e >> 1] = pack2<kBF16>(d0, d1);
         }
