@@ -130,7 +130,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const int64_t bh = static_cast<int64_t>(b) * p.H + h;
 #ifdef FA_TRACE
   const bool btr_on = p.trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 &&
-                      (warp == 12 || warp == 0 || warp == 8);
+                      (warp == 12 || warp == 0 || (warp >= 8 && warp < 12));
 #endif
 
   if (tid == 0) {
@@ -248,11 +248,11 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           FA_BTR(0, it, 5);
           if (it + 1 < n_iter) {
             mbar_wait(bar_do_full, (it + 1) & 1, 66);
+            FA_BTR(0, it, 7);
             mbar_wait(bar_drained, it & 1, 67);  // dQ(i) has left the dP^T columns
             tc_fence_after();
             FA_BTR(0, it, 6);
             issue_dp();
-            FA_BTR(0, it, 7);
           }
         }
       }
@@ -334,10 +334,10 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
       const int i = i_begin + it;
-      FA_BTR(2, it, 0);
+      if (dw == 0) FA_BTR(2, it, 0);
       mbar_wait(bar_dq, it & 1, 70);
       tc_fence_after();
-      FA_BTR(2, it, 1);
+      if (dw == 0) FA_BTR(2, it, 1);
       uint32_t v[kDP];
 #pragma unroll
       for (int cidx = 0; cidx < kDP / 32; ++cidx) tmem_ld_x32(tmem + lane_base + kColdQ + cidx * 32, v + cidx * 32);
@@ -345,7 +345,7 @@ fa_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_drained);
-      FA_BTR(2, it, 2);
+      FA_BTR(2, it, 2 + dw);  // (one stamp per drain warp)
       // registers -> this warp's swizzled fp32 staging tile [32 rows][32 columns] -> TMA reduce-add into
       // dq_acc[b,h, 32 rows, 32 columns] (rows >= Nq are clipped by the tensor map)
 #pragma unroll
