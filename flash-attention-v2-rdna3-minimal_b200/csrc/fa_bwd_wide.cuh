@@ -158,17 +158,17 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
   const float c = p.scale_log2;
   const int row_abs = row0 + r;
 
-  // L / D: per-lane scalars (mode dQ) or, one streamed tile ahead, the value this thread will stage (vector modes)
+  // -L / -D: per-lane scalars (mode dQ) or, one streamed tile ahead, the value this thread will stage (vector modes)
   float l_lane = 0.f, d_lane = 0.f, ld_next = 0.f;
   const float* ld_src = (tid < 64) ? p.lse : p.delta;
   if (!kVecLD) {
     if (row_abs < p.Nq) {
-      l_lane = p.lse[bh * p.Nq + row_abs];
-      d_lane = p.delta[bh * p.Nq + row_abs];
+      l_lane = -p.lse[bh * p.Nq + row_abs];
+      d_lane = -p.delta[bh * p.Nq + row_abs];
     }
   } else if (tid < 128 && n_iter > 0) {
     const int q = ct0 * kWideT + (tid & 63);
-    ld_next = (q < p.Nq) ? ld_src[bh * p.Nq + q] : 0.f;
+    ld_next = (q < p.Nq) ? -ld_src[bh * p.Nq + q] : 0.f;
   }
 
   int waited2 = 0;  // bar_mma2 phases thread 0 has observed (it must observe every phase in order)
@@ -180,7 +180,7 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
       sLD[tid] = ld_next;
       if (it + 1 < n_iter) {
         const int q = (ct + 1) * kWideT + (tid & 63);
-        ld_next = (q < p.Nq) ? ld_src[bh * p.Nq + q] : 0.f;
+        ld_next = (q < p.Nq) ? -ld_src[bh * p.Nq + q] : 0.f;
       }
     }
     __syncthreads();  // (A) L / D of this tile visible; every thread is done with the previous tile's scores
@@ -227,32 +227,46 @@ fa_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_res1,  // K (dV, dK)
       tmem_ld_x32(tmem + lane_base + kColS + half * 32, sv);
       if (kNeedDP) tmem_ld_x32(tmem + lane_base + kColP + half * 32, dv);
       tmem_wait_ld();
+      // P = 2^(S c + (-L)), dS = P (dP + (-D)): packed FFMA2 / FADD2 / FMUL2 (sLD, l_lane, d_lane hold the NEGATED values:
+      // the packed adds take no negate modifier); the mask is a block of its own that only diagonal / edge tiles execute
       uint32_t pk[16], pk2[16];
+      float pf[32];
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        float val[2], val2[2];
+        const int col = half * 32 + e;
+        float x0, x1;
+        ffma2(x0, x1, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]), c, c, kVecLD ? sLD[col] : l_lane,
+              kVecLD ? sLD[col + 1] : l_lane);
+        pf[e] = ex2_approx(x0);
+        pf[e + 1] = ex2_approx(x1);
+      }
+      if (need_mask) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int col = half * 32 + e + u;
-          const float lq = kVecLD ? sLD[col] : l_lane;
-          float pe = ex2_approx(fmaf(__uint_as_float(sv[e + u]), c, -lq));
-          if (need_mask) {
-            const int col_abs = ct * kWideT + col;
-            const int key = kVecLD ? row_abs : col_abs;
-            const int qrow = kVecLD ? col_abs : row_abs;
-            const bool ok = key < p.Nkv && qrow < p.Nq && (!kCausal || key <= qrow);
-            pe = ok ? pe : 0.f;
-          }
-          val[u] = pe;
-          val2[u] = 0.f;
-          if (kNeedDP) {
-            const float dq_ = kVecLD ? sLD[64 + col] : d_lane;
-            const float ds = pe * (__uint_as_float(dv[e + u]) - dq_);
-            if (kTwoOut) val2[u] = ds; else val[u] = ds;
-          }
+        for (int e = 0; e < 32; ++e) {
+          const int col_abs = ct * kWideT + half * 32 + e;
+          const int key = kVecLD ? row_abs : col_abs;
+          const int qrow = kVecLD ? col_abs : row_abs;
+          const bool ok = key < p.Nkv && qrow < p.Nq && (!kCausal || key <= qrow);
+          pf[e] = ok ? pf[e] : 0.f;
         }
-        pk[e >> 1] = pack2<kBF16>(val[0], val[1]);
-        if (kTwoOut) pk2[e >> 1] = pack2<kBF16>(val2[0], val2[1]);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        if (kNeedDP) {
+          const int col = half * 32 + e;
+          float d0, d1;
+          fadd2(d0, d1, __uint_as_float(dv[e]), __uint_as_float(dv[e + 1]), kVecLD ? sLD[64 + col] : d_lane,
+                kVecLD ? sLD[64 + col + 1] : d_lane);
+          fmul2(d0, d1, d0, d1, pf[e], pf[e + 1]);
+          if (kTwoOut) {
+            pk[e >> 1] = pack2<kBF16>(pf[e], pf[e + 1]);
+            pk2[e >> 1] = pack2<kBF16>(d0, d1);
+          } else {
+            pk[e >> 1] = pack2<kBF16>(d0, d1);
+          }
+        } else {
+          pk[e >> 1] = pack2<kBF16>(pf[e], pf[e + 1]);
+        }
       }
       // the 16-bit tile over the first 16 of my own 32 score columns (P, or dS in the one-output dK / dQ modes); mode dKV
       // puts dS over my dP columns likewise
