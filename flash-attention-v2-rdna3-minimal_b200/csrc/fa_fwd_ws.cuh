@@ -77,6 +77,9 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 // Turn-taking between the softmax groups of the two Q tiles (experiment): tile 1 starts its step on KV
 // tile j only after tile 0 has issued its last exponentials of step j, and tile 0 starts step j+1
 // only after tile 1's step j, so the two groups never compete for the MUFU.
+#ifndef FA_MAX_XCHG_SHARED
+#define FA_MAX_XCHG_SHARED 1
+#endif
 #ifndef FA_SEQ
 #define FA_SEQ 0
 #endif
@@ -161,10 +164,17 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   FA_TRS(0);
   // (ptxas schedules the MUFU instructions of the loop above BEHIND this barrier - SASS-checked in round 2 - so the
   // chain is max -> exchange -> exponentials; forcing them in front of it measured 4.5-8 % slower)
+#if FA_MAX_XCHG_SHARED
+  st_shared_f32(smem_u32(my_max), mx);
+  named_bar_sync(pair_bar, 64);
+  FA_TRS(1);
+  const float m_cand = fmaxf(fmaxf(mx, ld_shared_f32(smem_u32(other_max))), m_run);
+#else
   *my_max = mx;
   named_bar_sync(pair_bar, 64);
   FA_TRS(1);
   const float m_cand = fmaxf(fmaxf(mx, *other_max), m_run);
+#endif
   // both threads of the row see the same three numbers, so they take the same decision
   const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
   float alpha = 1.f;
