@@ -14,7 +14,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <algorithm>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -195,9 +197,12 @@ int choose_kernel_shape(const Problem& p) {
   // Causal too (the four Q tiles of a pair run in lock step over the tiles the last one needs): 688 vs 619 TFLOPS
   // at N=16384; small causal problems keep the 128-row grain of the one-tile kernel (415 vs 373 at N=4096).
   const long long blocks256 = static_cast<long long>(p.B) * p.H * ((p.Nq + 2 * fa::kTileM - 1) / (2 * fa::kTileM));
+  // The persistent kernel first: its cost model (estimate_costs) knows both one-shot alternatives, so at head dims
+  // <= 64 it takes the problems that lose a large part of their last round - the Stable-Diffusion shapes: B=2 H=10
+  // N=4096 D=64 is 2.16 rounds of CTA pairs, 123 vs 147 us; B=2 H=20 N=1024 D=64 24.9 vs 31.4 us.
+  if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   if (p.D <= 64 && tiles128 > 148 && p.Nkv >= 4 * fa::kTileN && (!p.causal || blocks256 >= 2 * 148))
     return FA_KERNEL_WS3;
-  if (sk_eligible(p, 148)) return FA_KERNEL_SK;  // re-checked against the real SM count at launch
   // Causal problems whose 256-row blocks all fit in one round: the launch lasts as long as its longest block, so
   // the one-tile arrangement's 128-row grain wins although it moves twice the K/V per Q tile.  Beyond one round
   // the two-tile kernel is ahead again - since round 2 causal launches run longest block first across heads
@@ -420,18 +425,24 @@ void release_sk_workspaces(int device) {
 // What the persistent kernel can run at all: non-causal, whole 256-row query blocks.
 bool sk_possible(const Problem& p) { return !p.causal && p.Nq % (2 * fa::kTileM) == 0; }
 
-// Cost model for the persistent kernel against the one-shot two-tile kernel, in units of one
-// "step" = the time the two-tile kernels need for one KV tile of a 256-row query block (~1.7 us):
+// Cost model for the persistent kernel against the one-shot two-tile kernels, in units of one
+// "step" = the time the two-tile kernel (ws) needs for one KV tile of a 256-row query block:
 //   one-shot (ws)    ceil(U / n_sm) rounds of T steps, ~2 steps of fixed cost per CTA (launch, prologue, first
 //                    loads, first softmax, epilogue, drain)
+//   early-S (ws3)    head dims <= 64 only, on CTA pairs: ceil(pairs / (n_sm / 2)) rounds of 0.83 T steps (866 vs 721
+//                    TFLOPS at N=16384) + ~4.5 steps per round (cluster start-up; B=2 H=10 N=4096 D=64: 147 vs 155 us)
 //   persistent (sk)  ceil(U T / n_sm) steps, ~1 step per unit boundary inside a CTA (pipelined: round-2 A/B on
-//                    whole units, 592 units on 148 SMs: 232 vs 236 us), ~8 steps when units are split between
-//                    CTAs (the partial round trip through L2 and the merge at the end of the range: round-2
-//                    timeline, tools/trace_sk.py), ~2 steps of fixed cost once
+//                    whole units, 592 units on 148 SMs: 232 vs 236 us; 0.75 for loops of fewer than 4 KV tiles), a
+//                    penalty when units are split between CTAs (the partial's round trip through L2 and the merge
+//                    at the end of the range: ~8 steps at head dim 128, ~4 at head dims <= 64 where the partial is
+//                    half the size; none when T = 1, where items are whole units), ~2 steps of fixed cost once
 // Fitted to profiles/r02_sweep_kernels.json (fp16 H=16 D=128, sk vs ws in us): N=2048 38.4 / 31.2, 4096 110.7 /
-// 112.1, 8192 397 / 431, 16384 1538 / 1545.
+// 112.1, 8192 397 / 431, 16384 1538 / 1545, and to the Stable-Diffusion shapes of tools/bench_sd_shapes.py
+// (profiles/r02_bench_sd_shapes_kernels.txt, sk / ws3 / ws in us): B=2 H=10 N=4096 D=64 123 / 147 / 155,
+// B=2 H=20 N=1024 D=64 24.9 / 31.4 / 31.6, B=2 H=8 N=4096 D=40 103 / 101 / 108, cross-attention (77 keys)
+// B=2 H=10 Nq=4096 D=64 13.2 / 19.3 / 16.2, D=128 14.8 / - / 20.0.
 struct KernelCosts {
-  double ws, sk;
+  double ws, sk, ws3;  // ws3 = +inf where that kernel does not apply
 };
 KernelCosts estimate_costs(const Problem& p, int n_sm) {
   const double T = static_cast<double>((p.Nkv + fa::kTileN - 1) / fa::kTileN);
@@ -439,17 +450,35 @@ KernelCosts estimate_costs(const Problem& p, int n_sm) {
   KernelCosts k;
   k.ws = static_cast<double>((U + n_sm - 1) / n_sm) * (T + 2.0);
   const double per_cta = std::ceil(static_cast<double>(U) * T / n_sm);
-  const bool split = (U % n_sm) != 0;
-  k.sk = per_cta + 1.0 * std::ceil(per_cta / T) + (split ? 8.0 : 0.0) + 2.0;
+  const bool split = (U % n_sm) != 0 && T > 1.0;
+  const double boundary = (T < 4.0) ? 0.75 : 1.0;
+  const double merge = (p.D <= 64) ? 4.0 : 8.0;
+  k.sk = per_cta + boundary * std::ceil(per_cta / T) + (split ? merge : 0.0) + 2.0;
+  k.ws3 = std::numeric_limits<double>::infinity();
+  if (p.D <= 64 && T >= 4.0 && n_sm >= 2) {
+    const long long pairs = (U + 1) / 2, slots = n_sm / 2;
+    k.ws3 = static_cast<double>((pairs + slots - 1) / slots) * (0.83 * T + 4.5);
+  }
   return k;
 }
 
 // shape-only eligibility (the SM count defaults to a B200's 148 when no device is consulted)
 bool sk_eligible(const Problem& p, int n_sm) {
   if (!sk_possible(p) || n_sm <= 0) return false;
-  if (p.Nkv < 4 * fa::kTileN) return false;  // units of a tile or two: nothing to split, only boundaries to pay for
+  // every 128-row tile gets an SM of its own in one round: the one-tile kernel's territory (choose_kernel_shape)
+  if (static_cast<long long>(p.B) * p.H * (p.Nq / fa::kTileM) <= n_sm) return false;
   const KernelCosts k = estimate_costs(p, n_sm);
-  return k.sk < 0.985 * k.ws;
+  // head dims <= 64: measured only with more units than SMs (fewer: every unit is shared by several CTAs and the chain
+  // of partials grows; the early-S kernel or the one-tile kernel serve those)
+  if (p.D <= 64 && static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM)) <= n_sm) return false;
+  if (p.Nkv < 4 * fa::kTileN) {
+    // Loops of a tile or two (cross-attention): nothing to split, but with more units than SMs a persistent CTA's
+    // unit boundary is cheaper than a CTA turnover (B=2 H=10 Nq=4096 Nkv=77: 13.2 vs 16.2 us at D=64, 14.8 vs 20.0 us
+    // at D=128; B=2 H=8 Nq=16384 D=40: 26.9 vs 48.6 us).  Only worth it beyond one round.
+    const long long U = static_cast<long long>(p.B) * p.H * (p.Nq / (2 * fa::kTileM));
+    if (U <= n_sm) return false;
+  }
+  return k.sk < 0.985 * std::min(k.ws, k.ws3);
 }
 
 template <int kDP, bool kBF16>

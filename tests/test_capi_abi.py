@@ -71,9 +71,16 @@ def _st(B, H, N, D):
         ((1, 2, 300, 300, 256), _capi.FA_KERNEL_WIDE),        # head dim 129..256: one Q tile, two S buffers
         ((1, 16, 4096, 4096, 160), _capi.FA_KERNEL_WIDE),     # bench_with_sdpa.py:259-261 sweep point D = 16 * 10
         ((1, 2, 300, 300, 264), _capi.FA_KERNEL_SIMT),        # head dim > 256
-        ((2, 10, 4096, 4096, 64), _capi.FA_KERNEL_WS3),       # SDXL-like head dim 64: P in spare TMEM, early S issue
+        ((2, 8, 4096, 4096, 40), _capi.FA_KERNEL_WS3),        # SD 1.5 head dim 40: P in spare TMEM, early S issue (256 units: 1.73 rounds of pairs)
         ((1, 16, 16384, 16384, 40), _capi.FA_KERNEL_WS3),
-        ((2, 10, 4096, 77, 64), _capi.FA_KERNEL_WS),          # SDXL cross-attention: one KV tile, the pair start-up does not pay
+        ((2, 10, 4096, 4096, 64), _capi.FA_KERNEL_SK),        # SDXL: 320 units = 2.16 rounds -> persistent kernel (123 vs 147 us)
+        ((2, 20, 1024, 1024, 64), _capi.FA_KERNEL_SK),        # SDXL 32x32 level: 160 units x 8 tiles (24.9 vs 31.4 us)
+        ((2, 10, 4096, 77, 64), _capi.FA_KERNEL_SK),          # SDXL cross-attention, 320 one-tile units: unit boundaries beat CTA turnover (13.2 vs 16.2 us)
+        ((2, 10, 4096, 77, 128), _capi.FA_KERNEL_SK),         # ... at head dim 128 too (14.8 vs 20.0 us)
+        ((3, 10, 1536, 300, 64), _capi.FA_KERNEL_WS),         # 180 units x 3 tiles: the split would cost more than the half-empty round
+        ((1, 4, 4096, 77, 64), _capi.FA_KERNEL_WIDE),         # 128 tiles: one round of one-tile CTAs, nothing for a persistent CTA to gain
+        ((1, 8, 4096, 77, 64), _capi.FA_KERNEL_WS),           # 128 units: one round of two-tile CTAs
+        ((1, 16, 2048, 2048, 64), _capi.FA_KERNEL_WS3),       # 128 units <= 148 SMs: never the persistent kernel at head dims <= 64
         ((1, 8, 1024, 1024, 64), _capi.FA_KERNEL_WIDE),       # 64 tiles: one round of one-tile CTAs still wins
         ((2, 4, 77, 300, 40), _capi.FA_KERNEL_TC1),
     ],

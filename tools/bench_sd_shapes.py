@@ -11,18 +11,21 @@ sys.path.insert(0, os.path.join(ROOT, "flash-attention-v2-rdna3-minimal_b200"))
 from rocwmma_fattn import _capi  # noqa: E402
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F  # noqa: E402
 
+KERNELS = os.environ.get("SD_KERNELS", "auto,ws").split(",")
 SHAPES = [  # B, H, Nq, Nkv, D
     (2, 10, 4096, 4096, 64), (2, 10, 4096, 77, 64), (2, 20, 1024, 1024, 64), (2, 20, 1024, 77, 64),
     (2, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
+    (2, 10, 4096, 77, 128), (1, 10, 4096, 4096, 64), (2, 8, 16384, 16384, 40), (2, 8, 16384, 77, 40),
 ]
 
 
 def timed(fn):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm up on the capture stream: per-stream workspaces are allocated outside capture
+        for _ in range(3):
+            fn()
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=side):
         keep = [fn() for _ in range(20)]
@@ -43,11 +46,12 @@ for (B, H, Nq, Nkv, D) in SHAPES:
     k, v = (torch.rand((B, H, Nkv, D), dtype=torch.float16, device="cuda") for _ in range(2))
     fl = 4.0 * B * H * Nq * Nkv * D
     row = []
-    for name in ("auto", "ws"):
-        prev = _capi.set_kernel({"auto": _capi.FA_KERNEL_AUTO, "ws": _capi.FA_KERNEL_WS}[name])
+    for name in KERNELS:
+        prev = _capi.set_kernel({"auto": _capi.FA_KERNEL_AUTO, "ws": _capi.FA_KERNEL_WS, "ws3": _capi.FA_KERNEL_WS3,
+                                 "sk": _capi.FA_KERNEL_SK, "wide": _capi.FA_KERNEL_WIDE}[name])
         try:
             ms = timed(lambda: F.apply(q, k, v, None, False))
-            row.append("%s %.4f ms %6.1f TFLOPS" % (name, ms, fl / ms / 1e9))
+            row.append("%s %.4f ms %5.1f TF" % (name, ms, fl / ms / 1e9))
         except RuntimeError as e:  # forced kernel cannot serve the head dim
             row.append("%s n/a" % name)
         finally:
@@ -56,4 +60,4 @@ for (B, H, Nq, Nkv, D) in SHAPES:
     DP = D + (-D) % 8
     sel = _capi.KERNEL_NAMES[_capi.select_kernel(B, H, Nq, Nkv, DP, (H * Nq * DP, Nq * DP, DP, 1), (H * Nkv * DP, Nkv * DP, DP, 1),
                                                   (H * Nkv * DP, Nkv * DP, DP, 1), (H * Nq * DP, Nq * DP, DP, 1), 0, False, D ** -0.5)]
-    print("%-26s -> %-5s | %s | %s | torch SDPA %.4f ms" % ((B, H, Nq, Nkv, D), sel, row[0], row[1], ms_t), flush=True)
+    print("%-26s -> %-5s | %s | torch SDPA %.4f ms" % ((B, H, Nq, Nkv, D), sel, " | ".join(row), ms_t), flush=True)
