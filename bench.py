@@ -312,9 +312,11 @@ def lib_sdpa(q, k, v, _mask, causal):
     return torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
 
 
-def pcie_probe(host_sets, dev, reps=3):
+def pcie_probe(host_sets, dev, reps=3, sync=None):
     """Ceiling of the end-to-end path on this box: the step's H2D bytes and D2H bytes as plain pinned
-    cudaMemcpyAsync on two streams (no kernels), wall clock.  Returns seconds per step."""
+    cudaMemcpyAsync on two streams (no kernels), wall clock.  Returns seconds per step.  `sync` (a barrier over
+    the ranks) is called before the timed repetitions so that every rank's copies contend with every other
+    rank's, as they do in the end-to-end run."""
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     dbuf = {n: tuple(torch.empty_like(t, device=dev) for t in hs) for n, hs in host_sets.items()}
 
@@ -331,6 +333,8 @@ def pcie_probe(host_sets, dev, reps=3):
         s_out.synchronize()
 
     one()
+    if sync is not None:
+        sync()
     t0 = time.perf_counter()
     for _ in range(reps):
         one()
@@ -638,7 +642,7 @@ def main():
     # sanity (outside the timed region): the host path delivered what the device path computes
     b_chk, n_chk = points[0]
     e2e_err = full_tensor_error(*(t.to(dev) for t in host[n_chk][:3]), host[n_chk][3].to(dev), False)
-    probe_s = pcie_probe(host, dev)
+    probe_s = pcie_probe(host, dev, reps=e2e_steps, sync=barrier)
     e2e_s, probe_s, e2e_err = reduce_max([e2e_s, probe_s, e2e_err])
     h2d = sum(3 * b * H * n * D * 2 for (b, n) in points)
     d2h = sum(b * H * n * D * 2 for (b, n) in points)
@@ -653,7 +657,8 @@ def main():
                    "pcie_ceiling_gbs": round((h2d + d2h) / probe_s / 1e9, 1),
                    "frac_of_pcie_ceiling": round(probe_s / e2e_s, 4),
                    "pcie_ceiling_note": "the step's H2D and D2H bytes as bare pinned cudaMemcpyAsync on two streams, "
-                                        "no kernels, same ranks concurrently",
+                                        "no kernels, all ranks concurrently (barrier before the timed repetitions, as "
+                                        "many repetitions as e2e steps)",
                    "max_abs_err_vs_fp32_first_point": float(f"{e2e_err:.3e}"),
                    "numa_bound_cpus": len(numa_cpus)}
     del host
