@@ -68,7 +68,7 @@ struct SkCfg {
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kStage = kKV + kStages * kTileBytes;  // O staging
   static constexpr int kBars = kStage + kTileBytes;
-  static constexpr int kNumBars = 22 + 2 * kStages;
+  static constexpr int kNumBars = 23 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;  // float [2 tile][2 half][128]; also row sums
   static constexpr int kTotal = kMax + 2 * 2 * 128 * 4;
   static_assert(kTotal <= 232448, "shared memory budget");
@@ -154,16 +154,17 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_q_free = [&](int t) { return smem_u32(&bars[14 + t]); };
   // The O staging tile is used in turns, numbered k = 2 * (final segments so far) + tile (producer parts
   // do not use it): the 8 softmax warps of the tile fill it and arrive on bar_stage_full (phase k); the store
-  // warp (warp 18) issues the TMA store, waits until it has read the tile and arrives on bar_stage_free.
+  // warp (warp 18) issues the TMA store, waits until it has read the tile and arrives on bar_stage_free(tile).
   const uint32_t bar_stage_full = smem_u32(&bars[16]);                   // 8 softmax warps
-  const uint32_t bar_stage_free = smem_u32(&bars[17]);                   // count 1
+  // "the store of tile t's turn has read the staging tile": count 1, one phase per final segment
+  auto bar_stage_free = [&](int t) { return smem_u32(&bars[t == 0 ? 17 : 22]); };
   // producer part (at most one per CTA): the 8 softmax warps of tile t have stored their partial; the store
   // warp then publishes it (flag, release at gpu scope) while the softmax warps move on
   auto bar_part_done = [&](int t) { return smem_u32(&bars[18 + t]); };   // 8 softmax warps, one phase
   // consumer part (at most one per CTA): the store warp has seen the flags of every producer part of tile t
   auto bar_parts_ready = [&](int t) { return smem_u32(&bars[20 + t]); };  // count 1, one phase
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[22 + s]); };     // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[22 + kS + s]); };  // tcgen05.commit
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[23 + s]); };     // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[23 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -194,7 +195,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_parts_ready(t), 1);
     }
     mbar_init(bar_stage_full, 8);
-    mbar_init(bar_stage_free, 1);
+    mbar_init(bar_stage_free(0), 1);
+    mbar_init(bar_stage_free(1), 1);
 #pragma unroll
     for (int s = 0; s < kS; ++s) {
       mbar_init(bar_kv_full(s), 1);
@@ -460,7 +462,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.sk_flags + (cta + i) * 2 + t), "r"(0)
                            : "memory");
             tma_store_wait_read();  // the staging tile may be rewritten once the store has read it
-            mbar_arrive(bar_stage_free);
+            mbar_arrive(bar_stage_free(t));
           }
         }
       }
@@ -509,9 +511,14 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       FA_SK_TR(1 + 3 * seg);
       const int z = opaque_zero();
       const int rz = r + z;
-      sFinal[(t * 2 + half) * 128 + rz] = l_run;
+      // Row sums cross over through the row-max slots (single-buffered here: no shared memory left at head dim 128),
+      // each thread writing into its PARTNER's slot and reading its own: the last accesses to the partner's slot were
+      // the partner's store before the last pair barrier and my own load after it, so this store is ordered behind
+      // both by the barrier and program order (a store into my own slot would only be ordered behind the partner's
+      // load of my maximum by a margin of time - compute-sanitizer racecheck reported exactly that pair).
+      sFinal[(t * 2 + (half ^ 1)) * 128 + rz] = l_run;
       named_bar_sync(pair_bar, 64);
-      float l_tot = l_run + sFinal[(t * 2 + (half ^ 1)) * 128 + rz];
+      float l_tot = l_run + sFinal[(t * 2 + half) * 128 + rz];
       const int kind = (t0 > 0) ? 1 : (n < T ? 2 : 0);
       const int unit = wk.unit(cta, G) + z;
       int row0, hh, bb;
@@ -583,8 +590,19 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         f_mine *= inv_l;
         mbar_wait(bar_o_final(t), seg & 1, 54 + t);
         tc_fence_after();
-        // my turn on the staging tile: the previous user's TMA store has read it
-        if (use > 0) mbar_wait(bar_stage_free, (use - 1) & 1, 57);
+        // my turn on the staging tile: the previous user's - the OTHER tile's - TMA store has read it.  One "free"
+        // barrier per tile: tile 0 in final segment fs waits for tile 1's turn of segment fs - 1, tile 1 for tile 0's
+        // turn of segment fs.  Each tile observed the other's preceding phase one turn earlier, so a parity wait can
+        // never mistake an older phase for the one it needs (with a single shared barrier, phases use - 2 and use
+        // have the same parity).
+        {
+          const int fs = use >> 1;
+          if (t == 0) {
+            if (fs > 0) mbar_wait(bar_stage_free(1), (fs - 1) & 1, 57);
+          } else {
+            mbar_wait(bar_stage_free(0), fs & 1, 57);
+          }
+        }
         uint8_t* stage = smem + C::kStage;
 #pragma unroll
         for (int cidx = 0; cidx < kOHalf / 32; ++cidx) {
