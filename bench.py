@@ -790,6 +790,30 @@ def main():
             del pool
         extras["f16_noncausal_unaligned_n"] = un
 
+        # the reference's use case (README.md:104-154 reports it/s inside ComfyUI): every attention call of one UNet
+        # evaluation through the ComfyUI-shaped hook (rocwmma_fattn.hooks.comfy_attention: [B, N, heads * dim] activations
+        # as BNHD views), next to torch SDPA on the same shapes - tools/bench_sd_unet.py, attention only
+        try:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("_bench_sd_unet", os.path.join(ROOT, "tools", "bench_sd_unet.py"))
+            sd = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(sd)
+            from rocwmma_fattn import hooks
+
+            stack = {"note": "attention calls of one UNet evaluation (batch 2, 77 text tokens, synthetic fp16 activations), one CUDA "
+                             "graph per stack, device events; attention only - no weights, not an end-to-end it/s"}
+            for model in sd.MODELS:
+                layers = sd.build_stack(model, dtype)
+                ms = sd.timed(lambda: sd.run_stack(layers, hooks.comfy_attention))
+                ms_t = sd.timed(lambda: sd.run_stack(layers, sd.sdpa_hook))
+                stack[model] = {"attn_calls": 2 * sum(nl for *_x, nl in sd.MODELS[model]), "attn_ms_per_step": round(ms, 4),
+                                "library_torch_sdpa_ms_per_step": round(ms_t, 4)}
+                del layers
+            extras["sd_attention_stack_comfy_hook"] = stack
+        except Exception as exc:  # secondary: never take the bench line down
+            extras["sd_attention_stack_comfy_hook"] = {"error": repr(exc)[:200]}
+
     if extras:
         line["config"]["extra_sweeps"] = extras
 
