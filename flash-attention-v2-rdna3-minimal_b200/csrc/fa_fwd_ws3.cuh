@@ -104,9 +104,15 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
     exp4(i, nmc);
   }
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+#if FA_MAX_XCHG_SHARED  // 32-bit shared-space accesses instead of generic ones (see ws_softmax_step)
+  st_shared_f32(smem_u32(my_max), mx);
+  named_bar_sync(pair_bar, 64);
+  const float m_cand = fmaxf(fmaxf(mx, ld_shared_f32(smem_u32(other_max))), m_run);
+#else
   *my_max = mx;
   named_bar_sync(pair_bar, 64);
   const float m_cand = fmaxf(fmaxf(mx, *other_max), m_run);
+#endif
   const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
   float alpha = 1.f;
   if (__any_sync(0xffffffffu, grow)) {
