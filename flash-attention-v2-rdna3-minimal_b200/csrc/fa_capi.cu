@@ -440,7 +440,9 @@ bool sk_possible(const Problem& p) { return !p.causal && p.Nq % (2 * fa::kTileM)
 // 112.1, 8192 397 / 431, 16384 1538 / 1545, and to the Stable-Diffusion shapes of tools/bench_sd_shapes.py
 // (profiles/r02_bench_sd_shapes_kernels.txt, sk / ws3 / ws in us): B=2 H=10 N=4096 D=64 123 / 147 / 155,
 // B=2 H=20 N=1024 D=64 24.9 / 31.4 / 31.6, B=2 H=8 N=4096 D=40 103 / 101 / 108, cross-attention (77 keys)
-// B=2 H=10 Nq=4096 D=64 13.2 / 19.3 / 16.2, D=128 14.8 / - / 20.0.
+// B=2 H=10 Nq=4096 D=64 13.2 / 19.3 / 16.2, D=128 14.8 / - / 20.0.  With the early S issue in the persistent kernel at
+// head dims <= 64 (third session): B=2 H=10 N=4096 D=64 113 / 148, B=1 H=10 N=4096 D=64 61 / 99, B=2 H=20 N=1024 D=64
+// 23.5 / 31.7, B=2 H=8 N=4096 D=40 94.9 / 100.0, B=2 H=8 N=16384 D=40 1330 / 1283.
 struct KernelCosts {
   double ws, sk, ws3;  // ws3 = +inf where that kernel does not apply
 };
@@ -453,7 +455,10 @@ KernelCosts estimate_costs(const Problem& p, int n_sm) {
   const bool split = (U % n_sm) != 0 && T > 1.0;
   const double boundary = (T < 4.0) ? 0.75 : 1.0;
   const double merge = (p.D <= 64) ? 4.0 : 8.0;
-  k.sk = per_cta + boundary * std::ceil(per_cta / T) + (split ? merge : 0.0) + 2.0;
+  // head dims <= 64: the persistent kernel issues S_t(g+1) ahead of PV_t(g) too (P in spare tensor memory), which makes
+  // its step 0.89 of the two-tile kernel's (the early-S kernel on CTA pairs: 0.83)
+  const double step = (p.D <= 64) ? 0.89 : 1.0;
+  k.sk = step * per_cta + boundary * std::ceil(per_cta / T) + (split ? merge : 0.0) + 2.0;
   k.ws3 = std::numeric_limits<double>::infinity();
   if (p.D <= 64 && T >= 4.0 && n_sm >= 2) {
     const long long pairs = (U + 1) / 2, slots = n_sm / 2;

@@ -33,6 +33,7 @@
 // fa_fwd_ws.cuh; barrier parities run on counters that continue across the units of a CTA.
 #pragma once
 #include "fa_fwd_ws.cuh"
+#include "fa_fwd_ws3.cuh"  // ws3_softmax_step: the early-S protocol at head dim 64
 
 namespace fa {
 
@@ -68,7 +69,7 @@ struct SkCfg {
   static constexpr int kKV = kQ + 2 * kTileBytes;
   static constexpr int kStage = kKV + kStages * kTileBytes;  // O staging
   static constexpr int kBars = kStage + kTileBytes;
-  static constexpr int kNumBars = 23 + 2 * kStages;
+  static constexpr int kNumBars = 27 + 2 * kStages;
   static constexpr int kMax = kBars + 8 * kNumBars + 16;  // float [2 tile][2 half][128]; also row sums
   static constexpr int kTotal = kMax + 2 * 2 * 128 * 4;
   static_assert(kTotal <= 232448, "shared memory budget");
@@ -128,6 +129,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   constexpr int kQ4 = kOHalf / 4;  // float4s of a partial row-half
   auto col_s = [](int t) -> uint32_t { return static_cast<uint32_t>(t) * 128u; };
   auto col_o = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u; };
+  constexpr bool kEarlyS = (kDP == 64);  // P outside the S columns, S_t(g+1) issued ahead of PV_t(g) (see the barrier map)
+  auto col_p = [](int t) -> uint32_t { return 256u + static_cast<uint32_t>(t) * 128u + 64u; };  // kEarlyS only
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -163,8 +166,14 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
   auto bar_part_done = [&](int t) { return smem_u32(&bars[18 + t]); };   // 8 softmax warps, one phase
   // consumer part (at most one per CTA): the store warp has seen the flags of every producer part of tile t
   auto bar_parts_ready = [&](int t) { return smem_u32(&bars[20 + t]); };  // count 1, one phase
-  auto bar_kv_full = [&](int s) { return smem_u32(&bars[23 + s]); };     // tx, count 1
-  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[23 + kS + s]); };  // tcgen05.commit
+  // Head dim 64 (kEarlyS): tensor memory has 128 spare columns, so P_t gets a region of its own next to O_t instead of
+  // overwriting S_t - the protocol of fa_fwd_ws3.cuh: the softmax warps signal "S_t(g) is in registers" (bar_s_read, 8 warps,
+  // per item) and the MMA thread issues S_t(g+1) at once, AHEAD of PV_t(g); a commit behind every PV_t(g) (bar_pv_done, per
+  // item) frees the P region and is what the rare O rescale waits for.
+  auto bar_s_read = [&](int t) { return smem_u32(&bars[23 + t]); };
+  auto bar_pv_done = [&](int t) { return smem_u32(&bars[25 + t]); };
+  auto bar_kv_full = [&](int s) { return smem_u32(&bars[27 + s]); };     // tx, count 1
+  auto bar_kv_empty = [&](int s) { return smem_u32(&bars[27 + kS + s]); };  // tcgen05.commit
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -193,6 +202,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_q_free(t), 1);
       mbar_init(bar_part_done(t), 8);
       mbar_init(bar_parts_ready(t), 1);
+      mbar_init(bar_s_read(t), 8);
+      mbar_init(bar_pv_done(t), 1);
     }
     mbar_init(bar_stage_full, 8);
     mbar_init(bar_stage_free(0), 1);
@@ -320,8 +331,8 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (last_of_seg) tc_commit(bar_q_free(t));
         };
         auto pv_step = [&](int t, uint32_t v_lo, int ks, uint32_t acc) {
-          umma_ts2(tmem + col_o(t), tmem + col_s(t) + (ks >> 2) * 64 + (ks & 3) * 8,
-                   v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
+          const uint32_t p_col = kEarlyS ? col_p(t) + ks * 8 : col_s(t) + (ks >> 2) * 64 + (ks & 3) * 8;
+          umma_ts2(tmem + col_o(t), tmem + p_col, v_lo + ((ks * 2048) >> 4), desc_hi, idesc_o, acc);
         };
         // g = running KV-tile count of this CTA (parity source of the per-item barriers)
         auto issue_pv = [&](int t, int vidx, int g, bool first, bool last) {
@@ -349,6 +360,7 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             pv_step(t, v_lo, 6, 1);
             pv_step(t, v_lo, 7, 1);
           }
+          if (kEarlyS) tc_commit(bar_pv_done(t));
           if (last) tc_commit(bar_o_final(t));
         };
 
@@ -376,6 +388,21 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const bool has_next = !last || more_segs;
             const bool next_is_new_seg = last && more_segs;
             const bool next_last_s = last ? (n_next == 1) : (j + 1 == n - 1);
+            // S_t(g+1): behind PV_t(g), or (kEarlyS) ahead of it as soon as the softmax warps hold S_t(g) in registers
+            auto next_s = [&](int t) {
+              if (t == 0) wait_kv(2 * g + 2);
+              if (next_is_new_seg) {
+                mbar_wait(bar_q_full(t), (seg + 1) & 1, 33 + t);
+                tc_fence_after();
+              }
+              if (kEarlyS) {
+                mbar_wait(bar_s_read(t), g & 1, 38 + t);
+                tc_fence_after();
+              }
+              issue_s(t, 2 * g + 2, next_last_s);
+              if (t == 1) release_kv(2 * g + 2);
+            };
+            if (kEarlyS && has_next) next_s(0);
             wait_kv(2 * g + 1);
             // O_t of the previous segment must have left TMEM before the first PV overwrites it
             if (first && seg > 0) {
@@ -383,28 +410,14 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
               tc_fence_after();
             }
             issue_pv(0, 2 * g + 1, g, first, last);
-            if (has_next) {
-              wait_kv(2 * g + 2);
-              if (next_is_new_seg) {
-                mbar_wait(bar_q_full(0), (seg + 1) & 1, 33);
-                tc_fence_after();
-              }
-              issue_s(0, 2 * g + 2, next_last_s);
-            }
+            if (has_next) next_s(kEarlyS ? 1 : 0);
             if (first && seg > 0) {
               mbar_wait(bar_tile_free(1), (seg - 1) & 1, 37);
               tc_fence_after();
             }
             issue_pv(1, 2 * g + 1, g, first, last);
             release_kv(2 * g + 1);
-            if (has_next) {
-              if (next_is_new_seg) {
-                mbar_wait(bar_q_full(1), (seg + 1) & 1, 34);
-                tc_fence_after();
-              }
-              issue_s(1, 2 * g + 2, next_last_s);
-              release_kv(2 * g + 2);
-            }
+            if (!kEarlyS && has_next) next_s(1);
           }
         }
       }
@@ -501,9 +514,23 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
         tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
         tmem_wait_ld();
-        ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, (t0 + j) * kTileN + half * 64, p.Nkv,
-                                    false, c, m_run, l_run, j > 0, my_max, other_max, pair_bar, bar_p_early(t),
-                                    bar_p_late(t), 0u, bar_p_mid(t));
+        if constexpr (kEarlyS) {
+          Ws3StepArgs a;  // (shared::cta addresses are valid shared::cluster addresses of the executing CTA)
+          a.bar_early = bar_p_early(t);
+          a.bar_mid = bar_p_mid(t);
+          a.bar_late = bar_p_late(t);
+          a.bar_s_read = bar_s_read(t);
+          a.bar_pv_done = bar_pv_done(t);
+          a.p_row = nullptr;
+          a.swz = 0;
+          a.tP = tmem + lane_base + col_p(t) + half * 32;
+          ws3_softmax_step<kDP, kBF16>(s, tS, tO, lane, (t0 + j) * kTileN + half * 64, p.Nkv, c, m_run, l_run, g, my_max,
+                                       other_max, pair_bar, a, false, 64, j > 0 ? 1 : 0);
+        } else {
+          ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, (t0 + j) * kTileN + half * 64, p.Nkv,
+                                      false, c, m_run, l_run, j > 0, my_max, other_max, pair_bar, bar_p_early(t),
+                                      bar_p_late(t), 0u, bar_p_mid(t));
+        }
       }
 
       // ---- end of the pass over this unit's KV range.  Everything the epilogue needs is derived here, behind

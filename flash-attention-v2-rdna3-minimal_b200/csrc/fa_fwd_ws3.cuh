@@ -51,8 +51,12 @@ template <int kDP, bool kBF16>
 __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int lane, int col0,
                                                  int Nkv, float c, float& m_run, float& l_run, int j,
                                                  float* my_max, const float* other_max, int pair_bar,
-                                                 const Ws3StepArgs& a, bool causal_tile = false, int lim_c = 64) {
+                                                 const Ws3StepArgs& a, bool causal_tile = false, int lim_c = 64,
+                                                 int have_o_flag = -1) {
   constexpr int kOHalf = kDP / 2;
+  // j is the parity source of the per-step barriers; O_t holds a partial sum when j > 0 - unless the caller runs several
+  // passes over one barrier sequence (the persistent kernel: j counts across units) and says so itself
+  const bool have_o = have_o_flag < 0 ? (j > 0) : (have_o_flag != 0);
   const bool tail = (col0 + 64 > Nkv);
   const bool masked = tail || causal_tile;
   int lim = 64;
@@ -120,7 +124,7 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
       alpha = ex2_approx((m_run - m_cand) * c);
       m_run = m_cand;
     }
-    if (j > 0) {
+    if (have_o) {
       mbar_wait(a.bar_pv_done, (j - 1) & 1, 44);  // S_t(j) was issued before PV_t(j-1): wait for PV_t(j-1) itself
       tc_fence_after();
 #pragma unroll 1

@@ -71,7 +71,8 @@ def _st(B, H, N, D):
         ((1, 2, 300, 300, 256), _capi.FA_KERNEL_WIDE),        # head dim 129..256: one Q tile, two S buffers
         ((1, 16, 4096, 4096, 160), _capi.FA_KERNEL_WIDE),     # bench_with_sdpa.py:259-261 sweep point D = 16 * 10
         ((1, 2, 300, 300, 264), _capi.FA_KERNEL_SIMT),        # head dim > 256
-        ((2, 8, 4096, 4096, 40), _capi.FA_KERNEL_WS3),        # SD 1.5 head dim 40: P in spare TMEM, early S issue (256 units: 1.73 rounds of pairs)
+        ((2, 8, 4096, 4096, 40), _capi.FA_KERNEL_SK),         # SD 1.5 head dim 40, 256 units = 1.73 rounds of pairs: persistent kernel (94.9 vs 100.0 us)
+        ((2, 8, 16384, 16384, 40), _capi.FA_KERNEL_WS3),      # 1024 units x 128 tiles, 6.9 rounds of pairs: the early-S kernel on CTA pairs (1283 vs 1330 us)
         ((1, 16, 16384, 16384, 40), _capi.FA_KERNEL_WS3),
         ((2, 10, 4096, 4096, 64), _capi.FA_KERNEL_SK),        # SDXL: 320 units = 2.16 rounds -> persistent kernel (123 vs 147 us)
         ((2, 20, 1024, 1024, 64), _capi.FA_KERNEL_SK),        # SDXL 32x32 level: 160 units x 8 tiles (24.9 vs 31.4 us)
