@@ -12,6 +12,10 @@ from rocwmma_fattn import _capi  # noqa: E402
 from rocwmma_fattn.FlashAttn import FlashAttentionFunction as F  # noqa: E402
 
 KERNELS = os.environ.get("SD_KERNELS", "auto,ws").split(",")
+if os.environ.get("SD_SHAPES"):  # "B,H,Nq,Nkv,D;B,H,..." replaces the built-in list
+    SHAPES_OVERRIDE = [tuple(int(x) for x in item.split(",")) for item in os.environ["SD_SHAPES"].split(";")]
+else:
+    SHAPES_OVERRIDE = None
 SHAPES = [  # B, H, Nq, Nkv, D
     (2, 10, 4096, 4096, 64), (2, 10, 4096, 77, 64), (2, 20, 1024, 1024, 64), (2, 20, 1024, 77, 64),
     (2, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
@@ -41,7 +45,7 @@ def timed(fn):
     return a.elapsed_time(b) / 100
 
 
-for (B, H, Nq, Nkv, D) in SHAPES:
+for (B, H, Nq, Nkv, D) in (SHAPES_OVERRIDE or SHAPES):
     q = torch.rand((B, H, Nq, D), dtype=torch.float16, device="cuda")
     k, v = (torch.rand((B, H, Nkv, D), dtype=torch.float16, device="cuda") for _ in range(2))
     fl = 4.0 * B * H * Nq * Nkv * D
