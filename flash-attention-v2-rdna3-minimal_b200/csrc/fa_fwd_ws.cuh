@@ -31,6 +31,8 @@
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 / kernel_bf16.cu:329-576 and the
 // device GEMM helpers (:115-302); see fa_fwd_tc.cuh for the serial version of the same algorithm.
 #pragma once
+#include <type_traits>
+
 #include "fa_fwd_tc.cuh"
 
 namespace fa {
@@ -77,6 +79,10 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 // Turn-taking between the softmax groups of the two Q tiles (experiment): tile 1 starts its step on KV
 // tile j only after tile 0 has issued its last exponentials of step j, and tile 0 starts step j+1
 // only after tile 1's step j, so the two groups never compete for the MUFU.
+// Peel the first KV tile of every pass into its own instantiation of the softmax step (kFirst, see ws_softmax_step).
+#ifndef FA_PEEL_FIRST
+#define FA_PEEL_FIRST 1
+#endif
 #ifndef FA_MAX_XCHG_SHARED
 #define FA_MAX_XCHG_SHARED 1
 #endif
@@ -104,7 +110,10 @@ constexpr int kPvParts = FA_PV_PARTS;
 //   have_o      O_t already holds a partial sum (not the first KV tile of this pass)
 //   bar_o       0, or the mbarrier (with parity o_parity) that tells PV(j-1) has left the tensor cores
 //   kPairArrive the P barriers are shared::cluster addresses in the leader CTA of a CTA pair (wide2 kernel)
-template <int kDP, bool kBF16, bool kPairArrive = false>
+//   kFirst      compile-time "first KV tile of a pass" (the kernels peel that step, FA_PEEL_FIRST): there is no running max to
+//               speculate against, so the row max is reduced first and every exponential is computed once, against the real
+//               max - no second tensor-memory load, no O to rescale.  have_o must be false.
+template <int kDP, bool kBF16, bool kPairArrive = false, bool kFirst = false>
 __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
@@ -158,7 +167,7 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
     mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
     mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
     mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
-    exp4(i, nmc);
+    if constexpr (!kFirst) exp4(i, nmc);
   }
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
   FA_TRS(0);
@@ -178,7 +187,13 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
   // both threads of the row see the same three numbers, so they take the same decision
   const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
   float alpha = 1.f;
-  if (__any_sync(0xffffffffu, grow)) {
+  if constexpr (kFirst) {
+    // (l_run is 0 and O_t empty: alpha is never used; s[] still holds the raw, masked scores)
+    if (grow) m_run = m_cand;
+    nmc = -m_run * c;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) exp4(i, nmc);
+  } else if (__any_sync(0xffffffffu, grow)) {
     // slow path (first tile; afterwards only when some row max grew by more than 2^8)
     if (grow) {
       alpha = ex2_approx((m_run - m_cand) * c);
@@ -584,8 +599,8 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_run = -INFINITY;
     float l_run = 0.f;  // partial row sum over my key half
 
-#pragma unroll 1
-    for (int j = 0; j < n; ++j) {
+    auto kv_step = [&](int j, auto first_tag) {
+      constexpr bool kFirstStep = decltype(first_tag)::value;
       FA_TR(tr_role, j, 0);
       mbar_wait_warp(bar_s_full(t), j & 1, 40 + t);
       tc_fence_after();
@@ -603,8 +618,8 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       FA_TR(tr_role, j, 2);
 
-      ws_softmax_step<kDP, kBF16>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
-                                  kCausal && (j == diag_j), c, m_run, l_run, j > 0,
+      ws_softmax_step<kDP, kBF16, false, kFirstStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
+                                  kCausal && (j == diag_j), c, m_run, l_run, kFirstStep ? false : (j > 0),
                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
                                   bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
                                   bar_p_mid(t)
@@ -613,7 +628,15 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #endif
                                   );
       FA_TR(tr_role, j, 6);
-    }
+    };
+#if FA_PEEL_FIRST
+    if (n > 0) kv_step(0, std::true_type{});
+#pragma unroll 1
+    for (int j = 1; j < n; ++j) kv_step(j, std::false_type{});
+#else
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) kv_step(j, std::false_type{});
+#endif
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (the tile's Q buffer) -> TMA store
     if (n > 0) {

@@ -47,7 +47,8 @@ struct Ws3StepArgs {
 // ws_softmax_step in fa_fwd_ws.cuh, non-causal).
 //   causal_tile / lim_c   this tile needs the causal mask: columns i >= lim_c of my half are hidden (lim_c <= 0:
 //                         the whole half - the lock-step extra tiles of the earlier Q tiles of a pair)
-template <int kDP, bool kBF16>
+//   kFirst                compile-time "first KV tile of a pass", as in ws_softmax_step (the persistent kernel peels it)
+template <int kDP, bool kBF16, bool kFirst = false>
 __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int lane, int col0,
                                                  int Nkv, float c, float& m_run, float& l_run, int j,
                                                  float* my_max, const float* other_max, int pair_bar,
@@ -105,7 +106,7 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
     mx1 = fmaxf(mx1, fmaxf(s[i + 1], s[i + 33]));
     mx2 = fmaxf(mx2, fmaxf(s[i + 2], s[i + 34]));
     mx3 = fmaxf(mx3, fmaxf(s[i + 3], s[i + 35]));
-    exp4(i, nmc);
+    if constexpr (!kFirst) exp4(i, nmc);
   }
   const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 #if FA_MAX_XCHG_SHARED  // 32-bit shared-space accesses instead of generic ones (see ws_softmax_step)
@@ -119,7 +120,12 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
 #endif
   const bool grow = (m_cand - m_run) * c > kRescaleThreshold;  // always true on the first tile
   float alpha = 1.f;
-  if (__any_sync(0xffffffffu, grow)) {
+  if constexpr (kFirst) {
+    if (grow) m_run = m_cand;  // (l_run is 0 and O_t empty: alpha is never used; s[] still holds the raw, masked scores)
+    nmc = -m_run * c;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) exp4(i, nmc);
+  } else if (__any_sync(0xffffffffu, grow)) {
     if (grow) {
       alpha = ex2_approx((m_run - m_cand) * c);
       m_run = m_cand;
