@@ -253,8 +253,9 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_run = -INFINITY;
     float l_run = 0.f;  // partial row sum over my key half
 
-    auto kv_step = [&](int j, auto first_tag) {
+    auto kv_step = [&](int j, auto first_tag, auto nomask_tag) {
       constexpr bool kFirstStep = decltype(first_tag)::value;
+      constexpr bool kNoMaskStep = decltype(nomask_tag)::value;
       const int buf = j & 1;
       const uint32_t tS = tmem + lane_base + buf * 128 + half * 64;  // my 64 S columns; P over [0,32)
       mbar_wait_warp(bar_s_full(buf), (j >> 1) & 1, 40);
@@ -263,19 +264,25 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS, reinterpret_cast<uint32_t*>(s));
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
-      ws_softmax_step<kDP, kBF16, false, kFirstStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
+      ws_softmax_step<kDP, kBF16, false, kFirstStep, kNoMaskStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
                                   kCausal && (j == qtile), c, m_run, l_run, kFirstStep ? false : (j > 0),
                                   my_max + buf * 256, other_max + buf * 256, pair_bar,
                                   bar_p_early(buf), bar_p_late(buf), 0u, bar_p_mid(buf), bar_o,
                                   static_cast<uint32_t>((j - 1) & 1));
     };
-#if FA_PEEL_FIRST
-    kv_step(0, std::true_type{});  // (n >= 1)
+    // (the causal diagonal and the ragged tail can only be the last tile: n = min(all tiles, qtile + 1))
+#if FA_PEEL_FIRST && FA_PEEL_MASK
+    kv_step(0, std::true_type{}, std::false_type{});  // (n >= 1)
 #pragma unroll 1
-    for (int j = 1; j < n; ++j) kv_step(j, std::false_type{});
+    for (int j = 1; j < n - 1; ++j) kv_step(j, std::false_type{}, std::true_type{});
+    if (n > 1) kv_step(n - 1, std::false_type{}, std::false_type{});
+#elif FA_PEEL_FIRST
+    kv_step(0, std::true_type{}, std::false_type{});  // (n >= 1)
+#pragma unroll 1
+    for (int j = 1; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
 #else
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) kv_step(j, std::false_type{});
+    for (int j = 0; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
 #endif
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (the Q buffer) -> TMA store

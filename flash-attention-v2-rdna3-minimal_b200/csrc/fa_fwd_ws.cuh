@@ -83,6 +83,10 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 #ifndef FA_PEEL_FIRST
 #define FA_PEEL_FIRST 1
 #endif
+// Interior KV tiles (not the first, not the last of a pass) run a softmax-step instantiation without mask code.
+#ifndef FA_PEEL_MASK
+#define FA_PEEL_MASK 1
+#endif
 #ifndef FA_MAX_XCHG_SHARED
 #define FA_MAX_XCHG_SHARED 1
 #endif
@@ -113,7 +117,9 @@ constexpr int kPvParts = FA_PV_PARTS;
 //   kFirst      compile-time "first KV tile of a pass" (the kernels peel that step, FA_PEEL_FIRST): there is no running max to
 //               speculate against, so the row max is reduced first and every exponential is computed once, against the real
 //               max - no second tensor-memory load, no O to rescale.  have_o must be false.
-template <int kDP, bool kBF16, bool kPairArrive = false, bool kFirst = false>
+//   kNoMask     compile-time "this tile is neither the last KV tile (ragged tail) nor the causal diagonal": the kernels run
+//               the interior tiles of a pass through an instantiation without any mask code (FA_PEEL_MASK)
+template <int kDP, bool kBF16, bool kPairArrive = false, bool kFirst = false, bool kNoMask = false>
 __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int half,
                                                 int r, int lane, int col0, int Nkv, bool diag,
                                                 float c, float& m_run, float& l_run, bool have_o,
@@ -122,8 +128,8 @@ __device__ __forceinline__ void ws_softmax_step(float (&s)[64], uint32_t tS, uin
                                                 uint32_t bar_turn = 0u, uint32_t bar_mid = 0u,
                                                 uint32_t bar_o = 0u, uint32_t o_parity = 0u FA_TRS_PARAM) {
   constexpr int kOHalf = kDP / 2;
-  const bool tail = (col0 + 64 > Nkv);
-  const bool masked = tail || diag;
+  const bool tail = !kNoMask && (col0 + 64 > Nkv);
+  const bool masked = !kNoMask && (tail || diag);
   int lim = 64;  // columns [0, lim) of my half are visible
   if (masked) {
     const int valid = tail ? (Nkv - col0) : 64;
@@ -599,8 +605,9 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
     float m_run = -INFINITY;
     float l_run = 0.f;  // partial row sum over my key half
 
-    auto kv_step = [&](int j, auto first_tag) {
+    auto kv_step = [&](int j, auto first_tag, auto nomask_tag) {
       constexpr bool kFirstStep = decltype(first_tag)::value;
+      constexpr bool kNoMaskStep = decltype(nomask_tag)::value;
       FA_TR(tr_role, j, 0);
       mbar_wait_warp(bar_s_full(t), j & 1, 40 + t);
       tc_fence_after();
@@ -618,7 +625,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       FA_TR(tr_role, j, 2);
 
-      ws_softmax_step<kDP, kBF16, false, kFirstStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
+      ws_softmax_step<kDP, kBF16, false, kFirstStep, kNoMaskStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
                                   kCausal && (j == diag_j), c, m_run, l_run, kFirstStep ? false : (j > 0),
                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
                                   bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
@@ -629,13 +636,19 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
                                   );
       FA_TR(tr_role, j, 6);
     };
-#if FA_PEEL_FIRST
-    if (n > 0) kv_step(0, std::true_type{});
+    // (the causal diagonal and the ragged tail can only be a pass's last tile: n = min(all tiles, diagonal + 1))
+#if FA_PEEL_FIRST && FA_PEEL_MASK
+    if (n > 0) kv_step(0, std::true_type{}, std::false_type{});
 #pragma unroll 1
-    for (int j = 1; j < n; ++j) kv_step(j, std::false_type{});
+    for (int j = 1; j < n - 1; ++j) kv_step(j, std::false_type{}, std::true_type{});
+    if (n > 1) kv_step(n - 1, std::false_type{}, std::false_type{});
+#elif FA_PEEL_FIRST
+    if (n > 0) kv_step(0, std::true_type{}, std::false_type{});
+#pragma unroll 1
+    for (int j = 1; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
 #else
 #pragma unroll 1
-    for (int j = 0; j < n; ++j) kv_step(j, std::false_type{});
+    for (int j = 0; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
 #endif
 
     // ---- epilogue: O / l -> 16 bit -> swizzled smem (the tile's Q buffer) -> TMA store

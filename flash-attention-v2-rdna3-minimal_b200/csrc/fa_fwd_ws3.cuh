@@ -48,7 +48,8 @@ struct Ws3StepArgs {
 //   causal_tile / lim_c   this tile needs the causal mask: columns i >= lim_c of my half are hidden (lim_c <= 0:
 //                         the whole half - the lock-step extra tiles of the earlier Q tiles of a pair)
 //   kFirst                compile-time "first KV tile of a pass", as in ws_softmax_step (the persistent kernel peels it)
-template <int kDP, bool kBF16, bool kFirst = false>
+//   kNoMask               compile-time "neither the ragged last KV tile nor a causal tile": no mask code (see ws_softmax_step)
+template <int kDP, bool kBF16, bool kFirst = false, bool kNoMask = false>
 __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, uint32_t tO, int lane, int col0,
                                                  int Nkv, float c, float& m_run, float& l_run, int j,
                                                  float* my_max, const float* other_max, int pair_bar,
@@ -58,8 +59,8 @@ __device__ __forceinline__ void ws3_softmax_step(float (&s)[64], uint32_t tS, ui
   // j is the parity source of the per-step barriers; O_t holds a partial sum when j > 0 - unless the caller runs several
   // passes over one barrier sequence (the persistent kernel: j counts across units) and says so itself
   const bool have_o = have_o_flag < 0 ? (j > 0) : (have_o_flag != 0);
-  const bool tail = (col0 + 64 > Nkv);
-  const bool masked = tail || causal_tile;
+  const bool tail = !kNoMask && (col0 + 64 > Nkv);
+  const bool masked = !kNoMask && (tail || causal_tile);
   int lim = 64;
   if (masked) {
     const int valid = tail ? (Nkv - col0) : 64;
