@@ -10,5 +10,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file gpurun_out/r02s3_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-extras > gpurun_out/r02s3_bench_under_ncu.log 2>&1
 tail -3 gpurun_out/r02s3_prof.log
 for n in ws_n16384 sk_n8192 sk_sdxl; do python tools/ncu_summary.py gpurun_out/r02s3_prof_$n.ncu-rep gpurun_out/r02s3_ncu_full_$n.json > /dev/null 2>&1; done
+rm -f gpurun_out/r02s3_prof_sk_n8192.ncu-rep gpurun_out/r02s3_prof_sk_sdxl.ncu-rep  # (64 MiB limit on what comes back; the ws capture is kept)
 ls -la gpurun_out/r02s3_* | tail -8
 wc -l gpurun_out/r02s3_launches_bench.csv
