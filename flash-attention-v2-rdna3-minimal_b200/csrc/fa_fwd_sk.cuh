@@ -527,10 +527,10 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
           a.tP = tmem + lane_base + col_p(t) + half * 32;
           ws3_softmax_step<kDP, kBF16, kFirstStep, kNoMaskStep>(s, tS, tO, lane, (t0 + j) * kTileN + half * 64, p.Nkv, c, m_run, l_run, g,
                                                    my_max, other_max, pair_bar, a, false, 64,
-                                                   (!kFirstStep && j > 0) ? 1 : 0);
+                                                   FA_PEEL_FIRST ? (kFirstStep ? 0 : 1) : (j > 0 ? 1 : 0));
         } else {
           ws_softmax_step<kDP, kBF16, false, kFirstStep, kNoMaskStep>(s, tS, tO, half, r, lane, (t0 + j) * kTileN + half * 64, p.Nkv,
-                                                         false, c, m_run, l_run, kFirstStep ? false : (j > 0), my_max,
+                                                         false, c, m_run, l_run, FA_PEEL_FIRST ? !kFirstStep : (j > 0), my_max,
                                                          other_max, pair_bar, bar_p_early(t), bar_p_late(t), 0u,
                                                          bar_p_mid(t));
         }

@@ -265,7 +265,7 @@ fa_fwd_wide_kernel(const __grid_constant__ CUtensorMap tmap_q,
       tmem_ld_x32(tS + 32, reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
       ws_softmax_step<kDP, kBF16, false, kFirstStep, kNoMaskStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
-                                  kCausal && (j == qtile), c, m_run, l_run, kFirstStep ? false : (j > 0),
+                                  kCausal && (j == qtile), c, m_run, l_run, FA_PEEL_FIRST ? !kFirstStep : (j > 0),
                                   my_max + buf * 256, other_max + buf * 256, pair_bar,
                                   bar_p_early(buf), bar_p_late(buf), 0u, bar_p_mid(buf), bar_o,
                                   static_cast<uint32_t>((j - 1) & 1));

@@ -87,6 +87,10 @@ constexpr int kEmuPairs = FA_EMU_PAIRS;
 #ifndef FA_PEEL_MASK
 #define FA_PEEL_MASK 1
 #endif
+// MMA thread: condition-free steady-state loop when both Q tiles visit every KV tile (experiment switch).
+#ifndef FA_MMA_FULL_LOOP
+#define FA_MMA_FULL_LOOP 1
+#endif
 #ifndef FA_MAX_XCHG_SHARED
 #define FA_MAX_XCHG_SHARED 1
 #endif
@@ -557,8 +561,39 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
           }
           release_kv(0);
         }
+#if FA_MMA_FULL_LOOP
+        // Both Q tiles visit every KV tile (non-causal, no padded second tile): all iterations but the last without the
+        // per-tile conditions of the generic loop below (the issuing thread sits on the P -> PV -> S chain of both tiles).
+        const bool full = !kCausal && n_t[0] == n_max && n_t[1] == n_max;
+        int j0 = 0;
+        if (full) {
 #pragma unroll 1
-        for (int j = 0; j < n_max; ++j) {
+          for (; j0 < n_max - 1; ++j0) {
+            const int j = j0, nx = j0 + 1;
+            FA_TR(2, j, 0);
+            wait_kv(2 * j + 1);
+            FA_TR(2, j, 1);
+            issue_pv(0, j);
+            FA_TR(2, j, 3);
+            wait_kv(2 * nx);
+            issue_s(0, nx);
+            FA_TR(2, j, 4);
+            issue_pv(1, j);
+            FA_TR(2, j, 6);
+            FA_TR(3, j, 3);
+            release_kv(2 * j + 1);
+            FA_TR(3, j, 4);
+            issue_s(1, nx);
+            FA_TR(3, j, 2);
+            release_kv(2 * nx);
+            FA_TR(2, j, 7);
+          }
+        }
+#else
+        const int j0 = 0;
+#endif
+#pragma unroll 1
+        for (int j = j0; j < n_max; ++j) {
           const int nx = j + 1;
           FA_TR(2, j, 0);
           wait_kv(2 * j + 1);
@@ -626,7 +661,7 @@ fa_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap_q,
       FA_TR(tr_role, j, 2);
 
       ws_softmax_step<kDP, kBF16, false, kFirstStep, kNoMaskStep>(s, tS, tO, half, r, lane, j * kTileN + half * 64, p.Nkv,
-                                  kCausal && (j == diag_j), c, m_run, l_run, kFirstStep ? false : (j > 0),
+                                  kCausal && (j == diag_j), c, m_run, l_run, FA_PEEL_FIRST ? !kFirstStep : (j > 0),
                                   my_max + (j & 1) * 512, other_max + (j & 1) * 512, pair_bar,
                                   bar_p_early(t), bar_p_late(t), kSeq ? bar_turn(t ^ 1) : 0u,
                                   bar_p_mid(t)
