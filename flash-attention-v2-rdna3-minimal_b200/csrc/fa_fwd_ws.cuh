@@ -28,6 +28,13 @@
 // the rest ("late"), so the tensor cores start on O += P V while the second half of the
 // exponentials is still in flight.
 //
+// The softmax step (ws_softmax_step) is compiled three times and a pass over the KV tiles runs
+//   first tile (kFirst: row max first, every exponential once) | interior tiles (kNoMask: no mask code) | last tile (generic)
+// - the causal diagonal and the ragged tail can only be the last tile.  The MMA thread likewise runs a loop without
+// per-tile conditions while both Q tiles have a further KV tile to visit.  What such splits do to ptxas' schedule of the
+// hot loop has to be measured per kernel: DESIGN.md 3.1 / 3.6 list where they won (here, wide, the persistent kernel's
+// head-dim-64 path) and where they lost (the persistent kernel's head-dim-128 path, the early-S kernel on pairs).
+//
 // Replaces /root/reference/rocwmma_fattn/kernel_fp16.cu:306-544 / kernel_bf16.cu:329-576 and the
 // device GEMM helpers (:115-302); see fa_fwd_tc.cuh for the serial version of the same algorithm.
 #pragma once
