@@ -35,6 +35,13 @@
 #include "fa_fwd_ws.cuh"
 #include "fa_fwd_ws3.cuh"  // ws3_softmax_step: the early-S protocol at head dim 64
 
+// Head-dim-128 path of the persistent kernel: when Nkv is a multiple of the KV tile there is no ragged tile anywhere, and
+// every step after a segment's first runs the mask-free instantiation in ONE loop (+0.35 % at N=8192 and on config 5's shards;
+// the first | interior | last split of the other kernels costs this path 2 %, see the loop).
+#ifndef FA_SK128_NOTAIL_LOOP
+#define FA_SK128_NOTAIL_LOOP 1
+#endif
+
 namespace fa {
 
 // Debug-only timeline (-DFA_TRACE): the leader thread of tile 0 stamps globaltimer into p.trace[cta * 32 + slot]:
@@ -546,8 +553,16 @@ fa_fwd_sk_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int j = 1; j < n - 1; ++j) kv_step(j, std::false_type{}, std::true_type{});
         if (n > 1) kv_step(n - 1, std::false_type{}, std::false_type{});
       } else {
+#if FA_SK128_NOTAIL_LOOP
+        if (p.Nkv % kTileN == 0) {  // no ragged tile anywhere: every further step of the segment is mask-free
 #pragma unroll 1
-        for (int j = 1; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
+          for (int j = 1; j < n; ++j) kv_step(j, std::false_type{}, std::true_type{});
+        } else
+#endif
+        {
+#pragma unroll 1
+          for (int j = 1; j < n; ++j) kv_step(j, std::false_type{}, std::false_type{});
+        }
       }
 #elif FA_PEEL_FIRST
       kv_step(0, std::true_type{}, std::false_type{});  // (a segment has at least one KV tile)
